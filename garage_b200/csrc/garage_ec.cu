@@ -1,0 +1,848 @@
+// garage_ec.cu -- C ABI (include/garage_ec.h) over the sm_100a kernels in rs_kernels.cuh.
+//
+// Product code: no CPU fallback, nothing from oracle/.  Every entry point returns a status
+// code and never throws/aborts across the boundary, mirroring the reference's
+// Result<_, Error> convention (src/util/error.rs:14-82).
+#include "../../include/garage_ec.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "rs_kernels.cuh"
+
+using namespace garage_ec;
+
+static_assert(GARAGE_EC_MAX_K == kMaxK && GARAGE_EC_MAX_M == kMaxM, "header/kernels limits differ");
+static_assert(GARAGE_EC_MAX_K == GARAGE_EC_MAX_K_HOST && GARAGE_EC_MAX_M == GARAGE_EC_MAX_M_HOST,
+              "header/gf256 limits differ");
+
+namespace {
+
+constexpr int kHostLanes = 3;                       // H2D / kernel / D2H overlap across chunks
+constexpr size_t kHostChunkBytes = 48ull << 20;     // target source bytes per pipeline chunk
+
+struct HostLane {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_buf = nullptr;  // chunk of shards (sources + outputs)
+    size_t d_cap = 0;
+    uint8_t *d_small = nullptr;  // shard_len / present / want / status / mismatch / plan
+    size_t small_cap = 0;
+};
+
+}  // namespace
+
+struct garage_ec_ctx {
+    int device = 0, k = 0, m = 0;
+    uint8_t P[kMaxM * kMaxK] = {0};
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int log2R = 0;
+    size_t smem_bytes = 0;
+    std::mutex host_mu;  // serialises HOST-mode calls (they share the lanes)
+    HostLane lanes[kHostLanes];
+    std::mutex misc_mu;  // timing list, last_error
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> free_events;
+    std::atomic<uint64_t> launches{0};
+    char last_error[256] = {0};
+};
+
+namespace {
+
+int set_cuda_error(garage_ec_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->misc_mu);
+        snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", what, cudaGetErrorString(e));
+    }
+    (void)cudaGetLastError();  // clear sticky-less errors
+    return e == cudaErrorMemoryAllocation ? GARAGE_EC_E_NOMEM : GARAGE_EC_E_CUDA;
+}
+
+#define CU_TRY(ctx, expr)                                          \
+    do {                                                           \
+        cudaError_t e__ = (expr);                                  \
+        if (e__ != cudaSuccess) return set_cuda_error(ctx, e__, #expr); \
+    } while (0)
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_geometry(const garage_ec_ctx *ctx, size_t stride, size_t n, int shards_per_stripe)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    if (stride == 0 || (stride & 15)) return GARAGE_EC_E_ALIGN;
+    if ((unsigned long long)stride * (unsigned long long)shards_per_stripe >= (1ull << 32))
+        return GARAGE_EC_E_INVALID;
+    if (n > 0xffffffffull) return GARAGE_EC_E_INVALID;
+    return GARAGE_EC_OK;
+}
+
+// ---- timing ---------------------------------------------------------------------------
+struct TimedLaunch {
+    garage_ec_ctx *ctx;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    TimedLaunch(garage_ec_ctx *c, cudaStream_t s) : ctx(c), st(s)
+    {
+        if (!ctx->timing) return;
+        std::lock_guard<std::mutex> g(ctx->misc_mu);
+        for (cudaEvent_t *e : {&a, &b}) {
+            if (!ctx->free_events.empty()) {
+                *e = ctx->free_events.back();
+                ctx->free_events.pop_back();
+            } else if (cudaEventCreate(e) != cudaSuccess) {
+                *e = nullptr;
+            }
+        }
+        if (a && b) cudaEventRecord(a, st);
+    }
+    ~TimedLaunch()
+    {
+        if (!a || !b) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> g(ctx->misc_mu);
+        ctx->pending.emplace_back(a, b);
+    }
+};
+
+// ---- kernel dispatch --------------------------------------------------------------------
+template <int K, int MODE>
+cudaError_t launch_apply_t(const garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t st)
+{
+    static std::atomic<int> configured_for_device{-1};  // per instantiation
+    auto kern = rs_apply_kernel<K, MODE>;
+    // opt-in shared memory size is a per-function, per-device attribute; setting it is cheap
+    // but not free, so remember the last device it was set for.
+    if (configured_for_device.load(std::memory_order_acquire) != ctx->device) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin);
+        if (e != cudaSuccess) return e;
+        configured_for_device.store(ctx->device, std::memory_order_release);
+    }
+    kern<<<ctx->sm_count, kThreads, ctx->smem_bytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_apply(garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t st)
+{
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    switch (p.k) {
+    case 4: return launch_apply_t<4, MODE>(ctx, p, st);
+    case 6: return launch_apply_t<6, MODE>(ctx, p, st);
+    case 10: return launch_apply_t<10, MODE>(ctx, p, st);
+    default: return launch_apply_t<0, MODE>(ctx, p, st);
+    }
+}
+
+uint32_t items_per_stripe(size_t stride) { return (uint32_t)((stride / 16 + 31) / 32); }
+
+// Device-resident encode (mode 0) / verify (mode 2) of n stripes, split so that
+// n * items_per_stripe stays below 2^32 and m > 4 runs in passes of 4 rows.
+int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pitch, uint8_t *dst,
+                size_t dst_pitch, uint32_t *mismatch, const uint32_t *shard_len, size_t stride,
+                size_t n, cudaStream_t st)
+{
+    const uint32_t ips = items_per_stripe(stride);
+    const size_t max_n = 0xffffffffull / ips;
+    TimedLaunch tl(ctx, st);
+    for (size_t s0 = 0; s0 < n; s0 += max_n) {
+        const size_t cnt = n - s0 < max_n ? n - s0 : max_n;
+        for (int r0 = 0; r0 < ctx->m; r0 += kRowsPerPass) {
+            ApplyParams p;
+            memset(&p, 0, sizeof(p));
+            p.src = src + s0 * src_pitch;
+            p.src_pitch = src_pitch;
+            p.dst = dst ? dst + s0 * dst_pitch + (size_t)r0 * stride : nullptr;
+            p.dst_pitch = dst_pitch;
+            p.shard_len = shard_len ? shard_len + s0 : nullptr;
+            p.mismatch = mismatch ? mismatch + s0 : nullptr;
+            p.stride = (uint32_t)stride;
+            p.n = (uint32_t)cnt;
+            p.k = (uint32_t)ctx->k;
+            p.rows = (uint32_t)(ctx->m - r0 < kRowsPerPass ? ctx->m - r0 : kRowsPerPass);
+            p.row_off = (uint32_t)r0;
+            p.items_per_stripe = ips;
+            p.log2R = (uint32_t)ctx->log2R;
+            for (uint32_t i = 0; i < p.rows; i++)
+                memcpy(p.coef + i * ctx->k, ctx->P + (r0 + i) * ctx->k, ctx->k);
+            cudaError_t e = mode == kModeEncode ? launch_apply<kModeEncode>(ctx, p, st)
+                                                : launch_apply<kModeVerify>(ctx, p, st);
+            if (e != cudaSuccess) return set_cuda_error(ctx, e, "rs_apply_kernel launch");
+        }
+    }
+    return GARAGE_EC_OK;
+}
+
+// Device-resident reconstruct.  plan/counter scratch supplied by the caller (device).
+int run_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present, const uint8_t *want,
+                    int32_t *status, const uint32_t *shard_len, size_t stride, size_t n,
+                    StripePlan *plan, uint32_t *counter, cudaStream_t st)
+{
+    PlanParams q;
+    memset(&q, 0, sizeof(q));
+    q.present = present;
+    q.want = want;
+    q.status = status;
+    q.plan = plan;
+    q.counter = counter;
+    q.n = (uint32_t)n;
+    q.k = (uint32_t)ctx->k;
+    q.m = (uint32_t)ctx->m;
+    memcpy(q.P, ctx->P, (size_t)ctx->k * ctx->m);
+    const unsigned blocks = (unsigned)((n + kPlanWarps - 1) / kPlanWarps);
+    rs_plan_kernel<<<blocks, kPlanWarps * 32, 0, st>>>(q);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "rs_plan_kernel launch");
+
+    TimedLaunch tl(ctx, st);
+    const size_t pitch = (size_t)(ctx->k + ctx->m) * stride;
+    for (int r0 = 0; r0 < ctx->m; r0 += kRowsPerPass) {
+        if (r0 > 0) {
+            e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), st);
+            if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMemsetAsync(counter)");
+        }
+        ApplyParams p;
+        memset(&p, 0, sizeof(p));
+        p.src = shards;
+        p.dst = shards;
+        p.src_pitch = p.dst_pitch = pitch;
+        p.shard_len = shard_len;
+        p.plan = plan;
+        p.counter = counter;
+        p.stride = (uint32_t)stride;
+        p.n = (uint32_t)n;
+        p.k = (uint32_t)ctx->k;
+        p.row_off = (uint32_t)r0;
+        p.log2R = (uint32_t)ctx->log2R;
+        e = launch_apply<kModePlan>(ctx, p, st);
+        if (e != cudaSuccess) return set_cuda_error(ctx, e, "rs_apply_kernel<plan> launch");
+    }
+    return GARAGE_EC_OK;
+}
+
+size_t plan_scratch_bytes(size_t n) { return n * sizeof(StripePlan) + 16; }
+
+// ---- host lanes -----------------------------------------------------------------------
+int lane_reserve(garage_ec_ctx *ctx, HostLane &L, size_t buf_bytes, size_t small_bytes)
+{
+    if (!L.stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    if (L.d_cap < buf_bytes) {
+        if (L.d_buf) cudaFree(L.d_buf);
+        L.d_buf = nullptr;
+        L.d_cap = 0;
+        CU_TRY(ctx, cudaMalloc(&L.d_buf, buf_bytes));
+        L.d_cap = buf_bytes;
+    }
+    if (L.small_cap < small_bytes) {
+        if (L.d_small) cudaFree(L.d_small);
+        L.d_small = nullptr;
+        L.small_cap = 0;
+        CU_TRY(ctx, cudaMalloc(&L.d_small, small_bytes));
+        L.small_cap = small_bytes;
+    }
+    return GARAGE_EC_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *P, int kind)
+{
+    if (!out) return GARAGE_EC_E_INVALID;
+    *out = nullptr;
+    if (k < 1 || k > kMaxK || m < 1 || m > kMaxM) return GARAGE_EC_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        (void)cudaGetLastError();
+        return GARAGE_EC_E_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) return GARAGE_EC_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GARAGE_EC_E_NODEVICE;
+    if (prop.major != 10) return GARAGE_EC_E_NODEVICE;  // built for sm_100a only
+    garage_ec_ctx *ctx = new (std::nothrow) garage_ec_ctx();
+    if (!ctx) return GARAGE_EC_E_NOMEM;
+    ctx->device = device;
+    ctx->k = k;
+    ctx->m = m;
+    if (P) {
+        memcpy(ctx->P, P, (size_t)k * m);
+    } else if (!h_build_matrix(k, m, kind, ctx->P)) {
+        delete ctx;
+        return GARAGE_EC_E_INVALID;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->log2R = -1;
+    for (int l = 5; l >= 0; l--)
+        if (smem_bytes_for(k, l) <= ctx->smem_optin) {
+            ctx->log2R = l;
+            break;
+        }
+    if (ctx->log2R < 0) {
+        delete ctx;
+        return GARAGE_EC_E_INVALID;
+    }
+    ctx->smem_bytes = smem_bytes_for(k, ctx->log2R);
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return GARAGE_EC_E_NODEVICE;
+    }
+    *out = ctx;
+    return GARAGE_EC_OK;
+}
+
+}  // namespace
+
+// ======================================================================= C ABI
+extern "C" {
+
+int garage_ec_abi_version(void) { return GARAGE_EC_ABI_VERSION; }
+
+const char *garage_ec_strerror(int code)
+{
+    switch (code) {
+    case GARAGE_EC_OK: return "ok";
+    case GARAGE_EC_E_INVALID: return "invalid argument or geometry";
+    case GARAGE_EC_E_CUDA: return "CUDA runtime error";
+    case GARAGE_EC_E_NOMEM: return "out of memory";
+    case GARAGE_EC_E_UNRECOVERABLE: return "stripe unrecoverable: fewer than k shards present";
+    case GARAGE_EC_E_NODEVICE: return "no usable sm_100 CUDA device (no CPU fallback)";
+    case GARAGE_EC_E_ALIGN: return "pointer or stride not 16-byte aligned";
+    default: return "unknown error";
+    }
+}
+
+int garage_ec_create(garage_ec_ctx **out, int cuda_device, int k, int m, int matrix_kind)
+{
+    if (matrix_kind != GARAGE_EC_VANDERMONDE && matrix_kind != GARAGE_EC_CAUCHY) {
+        if (out) *out = nullptr;
+        return GARAGE_EC_E_INVALID;
+    }
+    if (matrix_kind == GARAGE_EC_CAUCHY && k + m > 256) return GARAGE_EC_E_INVALID;
+    return create_common(out, cuda_device, k, m, nullptr, matrix_kind);
+}
+
+int garage_ec_create_with_matrix(garage_ec_ctx **out, int cuda_device, int k, int m,
+                                 const uint8_t *parity_rows)
+{
+    if (!parity_rows) {
+        if (out) *out = nullptr;
+        return GARAGE_EC_E_INVALID;
+    }
+    return create_common(out, cuda_device, k, m, parity_rows, 0);
+}
+
+void garage_ec_destroy(garage_ec_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (HostLane &L : ctx->lanes) {
+        if (L.stream) {
+            cudaStreamSynchronize(L.stream);
+            cudaStreamDestroy(L.stream);
+        }
+        if (L.d_buf) cudaFree(L.d_buf);
+        if (L.d_small) cudaFree(L.d_small);
+    }
+    for (auto &pr : ctx->pending) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+    delete ctx;
+}
+
+int garage_ec_matrix(const garage_ec_ctx *ctx, uint8_t *out_m_by_k)
+{
+    if (!ctx || !out_m_by_k) return GARAGE_EC_E_INVALID;
+    memcpy(out_m_by_k, ctx->P, (size_t)ctx->k * ctx->m);
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_params(const garage_ec_ctx *ctx, int *k, int *m, int *cuda_device)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    if (k) *k = ctx->k;
+    if (m) *m = ctx->m;
+    if (cuda_device) *cuda_device = ctx->device;
+    return GARAGE_EC_OK;
+}
+
+const char *garage_ec_last_error(const garage_ec_ctx *ctx) { return ctx ? ctx->last_error : ""; }
+
+uint32_t garage_ec_shard_len(uint32_t block_len, int k)
+{
+    if (k < 1) return 0;
+    return (uint32_t)(((unsigned long long)block_len + (unsigned)k - 1) / (unsigned)k);
+}
+
+size_t garage_ec_stride_for(uint32_t shard_len) { return align_up(shard_len ? shard_len : 1, 128); }
+
+uint64_t garage_ec_launch_count(const garage_ec_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int garage_ec_set_timing(garage_ec_ctx *ctx, int enabled)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    std::lock_guard<std::mutex> g(ctx->misc_mu);
+    ctx->timing = enabled != 0;
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_timing_read(garage_ec_ctx *ctx, double *total_ms, uint64_t *launches)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    cudaSetDevice(ctx->device);
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> todo;
+    {
+        std::lock_guard<std::mutex> g(ctx->misc_mu);
+        todo.swap(ctx->pending);
+    }
+    double sum = 0;
+    uint64_t cnt = 0;
+    int rc = GARAGE_EC_OK;
+    for (auto &pr : todo) {
+        float ms = 0;
+        cudaError_t e = cudaEventSynchronize(pr.second);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.first, pr.second);
+        if (e == cudaSuccess) {
+            sum += ms;
+            cnt++;
+        } else {
+            rc = set_cuda_error(ctx, e, "timing event");
+        }
+    }
+    {
+        std::lock_guard<std::mutex> g(ctx->misc_mu);
+        for (auto &pr : todo) {
+            ctx->free_events.push_back(pr.first);
+            ctx->free_events.push_back(pr.second);
+        }
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = cnt;
+    return rc;
+}
+
+int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes)
+{
+    if (!ctx || !out || !bytes) return GARAGE_EC_E_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return GARAGE_EC_OK;
+}
+
+void garage_ec_host_free(garage_ec_ctx *ctx, void *ptr)
+{
+    if (!ctx || !ptr) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(ptr);
+}
+
+int garage_ec_fill_random(garage_ec_ctx *ctx, uint8_t *dst_device, size_t len, uint64_t seed,
+                          uint64_t offset, void *cuda_stream)
+{
+    if (!ctx || !dst_device || (len & 7) || (offset & 7) ||
+        (reinterpret_cast<uintptr_t>(dst_device) & 7))
+        return GARAGE_EC_E_INVALID;
+    if (!len) return GARAGE_EC_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    fill_random_kernel<<<ctx->sm_count * 8, 256, 0, (cudaStream_t)cuda_stream>>>(
+        reinterpret_cast<unsigned long long *>(dst_device), len / 8, seed, offset / 8);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    CU_TRY(ctx, cudaGetLastError());
+    return GARAGE_EC_OK;
+}
+
+// --------------------------------------------------------------------------- ENCODE
+static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
+                       const uint32_t *shard_len, size_t stride, size_t n)
+{
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+    const size_t k = ctx->k, m = ctx->m;
+    size_t cs = kHostChunkBytes / (k * stride);
+    if (cs < 1) cs = 1;
+    if (cs > n) cs = n;
+    const size_t in_b = cs * k * stride, out_b = cs * m * stride;
+    for (HostLane &L : ctx->lanes) {
+        int rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16));
+        if (rc) return rc;
+    }
+    size_t c = 0;
+    for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
+        HostLane &L = ctx->lanes[c % kHostLanes];
+        const size_t cnt = n - s0 < cs ? n - s0 : cs;
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, data + s0 * k * stride, cnt * k * stride,
+                                    cudaMemcpyHostToDevice, L.stream));
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small, shard_len + s0, cnt * 4, cudaMemcpyHostToDevice,
+                                        L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small);
+        }
+        int rc = run_uniform(ctx, kModeEncode, L.d_buf, k * stride, L.d_buf + in_b, m * stride,
+                             nullptr, d_len, stride, cnt, L.stream);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(parity + s0 * m * stride, L.d_buf + in_b, cnt * m * stride,
+                                    cudaMemcpyDeviceToHost, L.stream));
+    }
+    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_encode(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
+                     const uint32_t *shard_len, size_t stride, size_t n_stripes, int mem_kind,
+                     void *cuda_stream)
+{
+    if (!ctx || (mem_kind != GARAGE_EC_MEM_HOST && mem_kind != GARAGE_EC_MEM_DEVICE))
+        return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_stripes, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_stripes == 0) return GARAGE_EC_OK;
+    if (!data || !parity) return GARAGE_EC_E_INVALID;
+    if (!aligned16(data) || !aligned16(parity)) return GARAGE_EC_E_ALIGN;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mem_kind == GARAGE_EC_MEM_HOST) return encode_host(ctx, data, parity, shard_len, stride, n_stripes);
+    return run_uniform(ctx, kModeEncode, data, (size_t)ctx->k * stride, parity, (size_t)ctx->m * stride,
+                       nullptr, shard_len, stride, n_stripes, (cudaStream_t)cuda_stream);
+}
+
+// --------------------------------------------------------------------------- VERIFY
+static int verify_host(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismatch,
+                       const uint32_t *shard_len, size_t stride, size_t n)
+{
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+    const size_t tot = ctx->k + ctx->m;
+    size_t cs = kHostChunkBytes / (tot * stride);
+    if (cs < 1) cs = 1;
+    if (cs > n) cs = n;
+    const size_t small = align_up(cs * 4, 16);
+    for (HostLane &L : ctx->lanes) {
+        int rc = lane_reserve(ctx, L, cs * tot * stride, 2 * small);
+        if (rc) return rc;
+    }
+    size_t c = 0;
+    for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
+        HostLane &L = ctx->lanes[c % kHostLanes];
+        const size_t cnt = n - s0 < cs ? n - s0 : cs;
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, shards + s0 * tot * stride, cnt * tot * stride,
+                                    cudaMemcpyHostToDevice, L.stream));
+        uint32_t *d_mm = reinterpret_cast<uint32_t *>(L.d_small);
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + small, shard_len + s0, cnt * 4,
+                                        cudaMemcpyHostToDevice, L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small + small);
+        }
+        CU_TRY(ctx, cudaMemsetAsync(d_mm, 0, cnt * 4, L.stream));
+        int rc = run_uniform(ctx, kModeVerify, L.d_buf, tot * stride, nullptr, 0, d_mm, d_len, stride,
+                             cnt, L.stream);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(mismatch + s0, d_mm, cnt * 4, cudaMemcpyDeviceToHost, L.stream));
+    }
+    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_verify(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismatch,
+                     const uint32_t *shard_len, size_t stride, size_t n_stripes, int mem_kind,
+                     void *cuda_stream)
+{
+    if (!ctx || (mem_kind != GARAGE_EC_MEM_HOST && mem_kind != GARAGE_EC_MEM_DEVICE))
+        return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_stripes, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_stripes == 0) return GARAGE_EC_OK;
+    if (!shards || !mismatch) return GARAGE_EC_E_INVALID;
+    if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mem_kind == GARAGE_EC_MEM_HOST) return verify_host(ctx, shards, mismatch, shard_len, stride, n_stripes);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU_TRY(ctx, cudaMemsetAsync(mismatch, 0, n_stripes * 4, st));
+    return run_uniform(ctx, kModeVerify, shards, (size_t)(ctx->k + ctx->m) * stride, nullptr, 0, mismatch,
+                       shard_len, stride, n_stripes, st);
+}
+
+// --------------------------------------------------------------------------- RECONSTRUCT
+static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
+                            const uint8_t *want, int32_t *status, const uint32_t *shard_len,
+                            size_t stride, size_t n)
+{
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+    const size_t k = ctx->k, tot = ctx->k + ctx->m;
+    size_t cs = kHostChunkBytes / (tot * stride);
+    if (cs < 1) cs = 1;
+    if (cs > n) cs = n;
+    // small buffer layout per lane: present | want | status | shard_len | plan+counter
+    const size_t o_present = 0, o_want = align_up(cs * tot, 16), o_status = o_want + align_up(cs * tot, 16);
+    const size_t o_len = o_status + align_up(cs * 4, 16), o_plan = o_len + align_up(cs * 4, 16);
+    const size_t small = o_plan + plan_scratch_bytes(cs);
+    for (HostLane &L : ctx->lanes) {
+        int rc = lane_reserve(ctx, L, cs * tot * stride, small);
+        if (rc) return rc;
+    }
+    std::vector<int32_t> st_host(status ? 0 : n);
+    int32_t *st_out = status ? status : st_host.data();
+    size_t c = 0;
+    for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
+        HostLane &L = ctx->lanes[c % kHostLanes];
+        const size_t cnt = n - s0 < cs ? n - s0 : cs;
+        uint8_t *d_sh = L.d_buf;
+        CU_TRY(ctx, cudaMemcpyAsync(d_sh, shards + s0 * tot * stride, cnt * tot * stride,
+                                    cudaMemcpyHostToDevice, L.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_present, present + s0 * tot, cnt * tot,
+                                    cudaMemcpyHostToDevice, L.stream));
+        const uint8_t *d_want = nullptr;
+        if (want) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_want, want + s0 * tot, cnt * tot,
+                                        cudaMemcpyHostToDevice, L.stream));
+            d_want = L.d_small + o_want;
+        }
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_len, shard_len + s0, cnt * 4, cudaMemcpyHostToDevice,
+                                        L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small + o_len);
+        }
+        StripePlan *d_plan = reinterpret_cast<StripePlan *>(L.d_small + o_plan);
+        uint32_t *d_counter = reinterpret_cast<uint32_t *>(L.d_small + o_plan + cnt * sizeof(StripePlan));
+        int rc = run_reconstruct(ctx, d_sh, L.d_small + o_present, d_want,
+                                 reinterpret_cast<int32_t *>(L.d_small + o_status), d_len, stride, cnt,
+                                 d_plan, d_counter, L.stream);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(st_out + s0, L.d_small + o_status, cnt * 4, cudaMemcpyDeviceToHost,
+                                    L.stream));
+        // copy back exactly the shards that were rebuilt
+        for (size_t s = s0; s < s0 + cnt; s++) {
+            const uint8_t *pr = present + s * tot;
+            size_t np = 0;
+            for (size_t i = 0; i < tot; i++) np += pr[i] ? 1 : 0;
+            if (np < k) continue;
+            const size_t len = shard_len ? shard_len[s] : stride;
+            const size_t bytes = align_up(len, 16);
+            for (size_t i = 0; i < tot; i++) {
+                if (pr[i] || (want && !want[s * tot + i])) continue;
+                CU_TRY(ctx, cudaMemcpyAsync(shards + (s * tot + i) * stride,
+                                            d_sh + ((s - s0) * tot + i) * stride, bytes,
+                                            cudaMemcpyDeviceToHost, L.stream));
+            }
+        }
+    }
+    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (size_t s = 0; s < n; s++)
+        if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
+                          const uint8_t *want, int32_t *status, const uint32_t *shard_len,
+                          size_t stride, size_t n_stripes, int mem_kind, void *cuda_stream)
+{
+    if (!ctx || (mem_kind != GARAGE_EC_MEM_HOST && mem_kind != GARAGE_EC_MEM_DEVICE))
+        return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_stripes, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_stripes == 0) return GARAGE_EC_OK;
+    if (!shards || !present) return GARAGE_EC_E_INVALID;
+    if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mem_kind == GARAGE_EC_MEM_HOST)
+        return reconstruct_host(ctx, shards, present, want, status, shard_len, stride, n_stripes);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    void *scratch = nullptr;
+    CU_TRY(ctx, cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
+    StripePlan *plan = reinterpret_cast<StripePlan *>(scratch);
+    uint32_t *counter =
+        reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scratch) + n_stripes * sizeof(StripePlan));
+    rc = run_reconstruct(ctx, shards, present, want, status, shard_len, stride, n_stripes, plan, counter, st);
+    cudaError_t e = cudaFreeAsync(scratch, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFreeAsync");
+    return GARAGE_EC_OK;
+}
+
+// --------------------------------------------------------------------------- BLOCK-LEVEL
+// H2D of one block split into k zero-padded shards at dst (device, shard layout).
+static int upload_block_split(garage_ec_ctx *ctx, const uint8_t *block, uint32_t block_len, size_t k,
+                              uint8_t *dst, size_t stride, uint32_t L, cudaStream_t st)
+{
+    const size_t full = L ? block_len / L : 0;  // shards completely covered by the block
+    const size_t rem = block_len - full * (size_t)L;
+    const size_t Lpad = align_up(L, 16);
+    if (full) {
+        CU_TRY(ctx, cudaMemcpy2DAsync(dst, stride, block, L, L, full < k ? full : k, cudaMemcpyHostToDevice, st));
+    }
+    if (full < k) {
+        uint8_t *d = dst + full * stride;
+        if (rem) CU_TRY(ctx, cudaMemcpyAsync(d, block + full * (size_t)L, rem, cudaMemcpyHostToDevice, st));
+        if (Lpad > rem) CU_TRY(ctx, cudaMemsetAsync(d + rem, 0, Lpad - rem, st));
+        for (size_t j = full + 1; j < k; j++) CU_TRY(ctx, cudaMemsetAsync(dst + j * stride, 0, Lpad, st));
+    }
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks, const uint32_t *block_len,
+                            size_t n_blocks, uint8_t *parity_out, size_t stride)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_blocks, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_blocks == 0) return GARAGE_EC_OK;
+    if (!blocks || !block_len || !parity_out) return GARAGE_EC_E_INVALID;
+    const size_t k = ctx->k, m = ctx->m;
+    for (size_t s = 0; s < n_blocks; s++) {
+        if (!blocks[s] && block_len[s]) return GARAGE_EC_E_INVALID;
+        if (garage_ec_shard_len(block_len[s], (int)k) > stride) return GARAGE_EC_E_INVALID;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+    size_t cs = kHostChunkBytes / (k * stride);
+    if (cs < 1) cs = 1;
+    if (cs > n_blocks) cs = n_blocks;
+    const size_t in_b = cs * k * stride, out_b = cs * m * stride;
+    for (HostLane &L : ctx->lanes) {
+        rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16));
+        if (rc) return rc;
+    }
+    std::vector<uint32_t> lens(cs * kHostLanes);
+    size_t c = 0;
+    for (size_t s0 = 0; s0 < n_blocks; s0 += cs, c++) {
+        const size_t lane_i = c % kHostLanes;
+        HostLane &L = ctx->lanes[lane_i];
+        const size_t cnt = n_blocks - s0 < cs ? n_blocks - s0 : cs;
+        // the pageable `lens` slot of this lane is reused: wait for the lane's previous chunk
+        if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        uint32_t *hl = lens.data() + lane_i * cs;
+        for (size_t s = 0; s < cnt; s++) {
+            hl[s] = garage_ec_shard_len(block_len[s0 + s], (int)k);
+            rc = upload_block_split(ctx, blocks[s0 + s], block_len[s0 + s], k, L.d_buf + s * k * stride,
+                                    stride, hl[s], L.stream);
+            if (rc) return rc;
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_small, hl, cnt * 4, cudaMemcpyHostToDevice, L.stream));
+        rc = run_uniform(ctx, kModeEncode, L.d_buf, k * stride, L.d_buf + in_b, m * stride, nullptr,
+                         reinterpret_cast<const uint32_t *>(L.d_small), stride, cnt, L.stream);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(parity_out + s0 * m * stride, L.d_buf + in_b, cnt * m * stride,
+                                    cudaMemcpyDeviceToHost, L.stream));
+    }
+    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *present,
+                            const uint32_t *block_len, size_t n_blocks, size_t stride,
+                            uint8_t *const *blocks_out, int32_t *status)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_blocks, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_blocks == 0) return GARAGE_EC_OK;
+    if (!shards || !present || !block_len || !blocks_out) return GARAGE_EC_E_INVALID;
+    if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
+    const size_t k = ctx->k, tot = ctx->k + ctx->m;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+
+    // stripes with an absent data shard go to the GPU; the rest is a host-side join
+    std::vector<size_t> need;
+    bool any_bad = false;
+    for (size_t s = 0; s < n_blocks; s++) {
+        const uint8_t *pr = present + s * tot;
+        size_t np = 0;
+        bool data_missing = false;
+        for (size_t i = 0; i < tot; i++) np += pr[i] ? 1 : 0;
+        for (size_t j = 0; j < k; j++) data_missing |= !pr[j];
+        if (garage_ec_shard_len(block_len[s], (int)k) > stride) return GARAGE_EC_E_INVALID;
+        if (np < k) {
+            if (status) status[s] = GARAGE_EC_E_UNRECOVERABLE;
+            any_bad = true;
+            continue;
+        }
+        if (status) status[s] = 0;
+        if (data_missing) need.push_back(s);
+    }
+    size_t cs = kHostChunkBytes / (tot * stride);
+    if (cs < 1) cs = 1;
+    if (!need.empty()) {
+        if (cs > need.size()) cs = need.size();
+        const size_t o_present = 0, o_want = align_up(cs * tot, 16), o_status = o_want + align_up(cs * tot, 16);
+        const size_t o_len = o_status + align_up(cs * 4, 16), o_plan = o_len + align_up(cs * 4, 16);
+        const size_t small = o_plan + plan_scratch_bytes(cs);
+        for (HostLane &L : ctx->lanes) {
+            rc = lane_reserve(ctx, L, cs * tot * stride, small);
+            if (rc) return rc;
+        }
+        std::vector<uint8_t> h_small((2 * cs * tot + cs * 4) * kHostLanes);
+        size_t c = 0;
+        for (size_t q0 = 0; q0 < need.size(); q0 += cs, c++) {
+            const size_t lane_i = c % kHostLanes;
+            HostLane &L = ctx->lanes[lane_i];
+            const size_t cnt = need.size() - q0 < cs ? need.size() - q0 : cs;
+            if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+            uint8_t *hp = h_small.data() + lane_i * (2 * cs * tot + cs * 4);
+            uint8_t *hw = hp + cs * tot;
+            uint32_t *hl = reinterpret_cast<uint32_t *>(hw + cs * tot);
+            for (size_t q = 0; q < cnt; q++) {
+                const size_t s = need[q0 + q];
+                memcpy(hp + q * tot, present + s * tot, tot);
+                for (size_t i = 0; i < tot; i++) hw[q * tot + i] = i < k ? 1 : 0;  // data shards only
+                hl[q] = garage_ec_shard_len(block_len[s], (int)k);
+                CU_TRY(ctx, cudaMemcpyAsync(L.d_buf + q * tot * stride, shards + s * tot * stride,
+                                            tot * stride, cudaMemcpyHostToDevice, L.stream));
+            }
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_present, hp, cnt * tot, cudaMemcpyHostToDevice, L.stream));
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_want, hw, cnt * tot, cudaMemcpyHostToDevice, L.stream));
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_len, hl, cnt * 4, cudaMemcpyHostToDevice, L.stream));
+            StripePlan *d_plan = reinterpret_cast<StripePlan *>(L.d_small + o_plan);
+            uint32_t *d_counter = reinterpret_cast<uint32_t *>(L.d_small + o_plan + cnt * sizeof(StripePlan));
+            rc = run_reconstruct(ctx, L.d_buf, L.d_small + o_present, L.d_small + o_want,
+                                 reinterpret_cast<int32_t *>(L.d_small + o_status),
+                                 reinterpret_cast<const uint32_t *>(L.d_small + o_len), stride, cnt, d_plan,
+                                 d_counter, L.stream);
+            if (rc) return rc;
+            // rebuilt data shards land directly in the output blocks
+            for (size_t q = 0; q < cnt; q++) {
+                const size_t s = need[q0 + q];
+                const size_t Ls = hl[q];
+                for (size_t j = 0; j < k; j++) {
+                    if (present[s * tot + j]) continue;
+                    const size_t off = j * Ls;
+                    if (off >= block_len[s]) continue;
+                    const size_t have = block_len[s] - off < Ls ? block_len[s] - off : Ls;
+                    CU_TRY(ctx, cudaMemcpyAsync(blocks_out[s] + off, L.d_buf + (q * tot + j) * stride, have,
+                                                cudaMemcpyDeviceToHost, L.stream));
+                }
+            }
+        }
+    }
+    // host-side join of the data shards that did arrive (framing: block = shard0|shard1|...)
+    for (size_t s = 0; s < n_blocks; s++) {
+        const uint8_t *pr = present + s * tot;
+        size_t np = 0;
+        for (size_t i = 0; i < tot; i++) np += pr[i] ? 1 : 0;
+        if (np < k) continue;
+        const size_t Ls = garage_ec_shard_len(block_len[s], (int)k);
+        for (size_t j = 0; j < k; j++) {
+            if (!pr[j]) continue;
+            const size_t off = j * Ls;
+            if (off >= block_len[s]) continue;
+            const size_t have = block_len[s] - off < Ls ? block_len[s] - off : Ls;
+            memcpy(blocks_out[s] + off, shards + (s * tot + j) * stride, have);
+        }
+    }
+    if (!need.empty())
+        for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    return any_bad ? GARAGE_EC_E_UNRECOVERABLE : GARAGE_EC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,520 @@
+// rs_kernels.cuh -- sm_100a kernels of the Garage erasure-coding block path.
+//
+// What they compute (normative definition: DESIGN.md "Arithmetic", oracle/rs_oracle.h):
+//     out[i][t] = XOR_j C[i][j] * src[j][t]         over GF(2^8)/0x11D, byte-wise
+// for rows i of a small coefficient matrix C (the parity rows P for encode/verify, a
+// per-stripe composed decode matrix for reconstruct) and the k source shards of a stripe.
+// Reference call sites this replaces work at: BlockManager::rpc_put_block
+// (src/block/manager.rs:366-408), rpc_get_raw_block_internal (manager.rs:276-339),
+// BlockResyncManager::resync_block (src/block/resync.rs:460-500), DataBlock::verify /
+// ScrubWorker::work (src/block/block.rs:69-83, src/block/repair.rs:438-490).
+//
+// Design (DESIGN.md "Kernel"):
+//  * HBM-bound byte work, no tensor cores.  The per-byte GF multiply-accumulate for up to 4
+//    output rows is ONE shared-memory lookup: T_j[x] = {C0j*x, C1j*x, C2j*x, C3j*x} packed in
+//    a 32-bit word, so a data byte costs one LDS + one XOR for all four rows.
+//  * Random byte indices would bank-conflict ~3.5-way on a plain 256-word table.  Each table
+//    is therefore replicated R times with replica g = lane % R living in banks
+//    {g, g+R, ...}: word address = (j*256 + x)*R + g.  R = 16 (k <= 13): two lanes share two
+//    banks -> 1.5 wavefronts/LDS expected; R = 32 (k <= 6): lane-private banks, conflict-free.
+//  * log/antilog tables sit in __constant__ memory and are copied to shared memory; they are
+//    only used to BUILD the product tables (once per launch for encode/verify, once per
+//    change of erasure pattern for reconstruct), never in the streaming loop.
+//  * Streaming loop: one 16-byte column of all k shards per thread (coalesced 512 B per warp
+//    per shard, ld.global.nc.L1::no_allocate.v4), 16 lookups per shard, 4x4 byte transposes
+//    with PRMT, one 16-byte st.global.cs per output row.
+//  * Persistent grid: one CTA per SM (tables fill shared memory), work items handed to warps
+//    (encode/verify) or to CTAs through an atomic counter (reconstruct).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gf256.h"
+
+namespace garage_ec {
+
+constexpr int kThreads = 512;  // threads per CTA (16 warps); 1 CTA per SM
+constexpr int kMaxK = 32;
+constexpr int kMaxM = 8;
+constexpr int kRowsPerPass = 4;  // output rows packed in one 32-bit table word
+
+__constant__ uint8_t c_gf_exp[512] = GARAGE_EC_GF_EXP_INIT;
+__constant__ uint8_t c_gf_log[256] = GARAGE_EC_GF_LOG_INIT;
+
+enum ApplyMode { kModeEncode = 0, kModePlan = 1, kModeVerify = 2 };
+
+// Per-stripe decode plan, produced by rs_plan_kernel, consumed by rs_apply_kernel<kModePlan>.
+struct __align__(16) StripePlan {
+    unsigned long long key_present;  // bit i: shard i present
+    unsigned long long key_out;      // bit i: shard i is rebuilt
+    uint8_t nrows;                   // number of shards rebuilt (0..m)
+    uint8_t unrecoverable;           // 1 if < k present
+    uint8_t pad[6];
+    uint8_t surv[kMaxK];           // source shard indices (first k present)
+    uint8_t out_idx[kMaxM];        // rebuilt shard indices
+    uint8_t coef[kMaxM][kMaxK];  // out[r] = XOR_j coef[r][j] * shard[surv[j]]
+};
+
+struct ApplyParams {
+    const uint8_t *src;            // stripe s source base = src + s*src_pitch
+    uint8_t *dst;                  // stripe s output base = dst + s*dst_pitch
+    unsigned long long src_pitch;  // bytes
+    unsigned long long dst_pitch;
+    const uint32_t *shard_len;  // device, nullable (=> stride)
+    const StripePlan *plan;     // kModePlan
+    uint32_t *mismatch;         // kModeVerify
+    uint32_t *counter;          // kModePlan dynamic scheduler
+    uint32_t stride;            // bytes between shards
+    uint32_t n;                 // stripes
+    uint32_t k;                 // sources
+    uint32_t rows;              // outputs this pass (<= 4), uniform modes
+    uint32_t row_off;           // first output row of this pass
+    uint32_t items_per_stripe;  // ceil(ceil(stride/16)/32), uniform modes
+    uint32_t log2R;             // table replication
+    uint8_t coef[kRowsPerPass * kMaxK];  // uniform modes: coef[i*k + j]
+};
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(void *p, const uint4 &v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+// zero the bytes at positions >= nbytes (0 < nbytes < 16) of a 16-byte vector
+__device__ __forceinline__ uint4 mask_tail(uint4 v, uint32_t nbytes)
+{
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int lo = 4 * i;
+        if ((int)nbytes <= lo) w[i] = 0;
+        else if ((int)nbytes < lo + 4) w[i] &= 0xffffffffu >> (8 * (lo + 4 - (int)nbytes));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 4x4 byte transpose: a[p] holds {row0,row1,row2,row3} bytes of byte column p;
+// returns r[i] = bytes of row i for columns 0..3.
+__device__ __forceinline__ void transpose4x4(const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                             const uint32_t a3, uint32_t &r0, uint32_t &r1,
+                                             uint32_t &r2, uint32_t &r3)
+{
+    const uint32_t t0 = __byte_perm(a0, a1, 0x5140);  // a0.b0 a1.b0 a0.b1 a1.b1
+    const uint32_t t1 = __byte_perm(a2, a3, 0x5140);
+    const uint32_t t2 = __byte_perm(a0, a1, 0x7362);  // a0.b2 a1.b2 a0.b3 a1.b3
+    const uint32_t t3 = __byte_perm(a2, a3, 0x7362);
+    r0 = __byte_perm(t0, t1, 0x5410);
+    r1 = __byte_perm(t0, t1, 0x7632);
+    r2 = __byte_perm(t2, t3, 0x5410);
+    r3 = __byte_perm(t2, t3, 0x7632);
+}
+
+// ------------------------------------------------------------------ shared memory carve-up
+struct SmemLayout {
+    // dynamic smem: [tables: k*256*R words][exp 512][log 256][src_off 32 u32][dst_off 4 u32]
+    //               [coef 4*32][sched 1 u32]
+    uint32_t *tab;
+    uint8_t *gf_exp;
+    uint8_t *gf_log;
+    uint32_t *src_off;
+    uint32_t *dst_off;
+    uint8_t *coef;
+    uint32_t *sched;
+};
+constexpr size_t kSmemAux = 512 + 256 + kMaxK * 4 + kRowsPerPass * 4 + kRowsPerPass * kMaxK + 16;
+__host__ __device__ inline size_t smem_bytes_for(int k, int log2R)
+{
+    return (size_t)k * 256 * 4 * ((size_t)1 << log2R) + kSmemAux;
+}
+
+__device__ __forceinline__ SmemLayout carve(unsigned char *base, uint32_t k, uint32_t log2R)
+{
+    SmemLayout L;
+    L.tab = reinterpret_cast<uint32_t *>(base);
+    unsigned char *p = base + ((size_t)k * 256 * 4 << log2R);
+    L.gf_exp = p;
+    p += 512;
+    L.gf_log = p;
+    p += 256;
+    L.src_off = reinterpret_cast<uint32_t *>(p);
+    p += kMaxK * 4;
+    L.dst_off = reinterpret_cast<uint32_t *>(p);
+    p += kRowsPerPass * 4;
+    L.coef = p;
+    p += kRowsPerPass * kMaxK;
+    L.sched = reinterpret_cast<uint32_t *>(p);
+    return L;
+}
+
+// Build the replicated product tables for `rows` (<=4) coefficient rows coef[i*cstride + j].
+// Caller syncs before (old tables idle, coef visible) and after.
+__device__ __forceinline__ void build_tables(const SmemLayout &L, const uint8_t *coef, uint32_t cstride,
+                                             uint32_t k, uint32_t rows, uint32_t log2R)
+{
+    const uint32_t R = 1u << log2R;
+    for (uint32_t e = threadIdx.x; e < k * 256; e += kThreads) {
+        const uint32_t j = e >> 8, x = e & 255;
+        uint32_t w = 0;
+        if (x) {
+            const uint32_t lx = L.gf_log[x];
+#pragma unroll
+            for (uint32_t i = 0; i < kRowsPerPass; i++) {
+                if (i < rows) {
+                    const uint32_t c = coef[i * cstride + j];
+                    if (c) w |= (uint32_t)L.gf_exp[L.gf_log[c] + lx] << (8 * i);
+                }
+            }
+        }
+        uint32_t *dst = L.tab + ((size_t)e << log2R);
+        if (R >= 4) {
+            const uint4 v = make_uint4(w, w, w, w);
+            for (uint32_t g = 0; g < R; g += 4) *reinterpret_cast<uint4 *>(dst + g) = v;
+        } else {
+            for (uint32_t g = 0; g < R; g++) dst[g] = w;
+        }
+    }
+}
+
+// 16 table lookups for one 16-byte vector of source j; acc[4*w + p] ^= T_j[byte p of word w]
+template <bool kFirst>
+__device__ __forceinline__ void lookup16(uint32_t (&acc)[16], const uint4 &d, uint32_t tab_j_lane,
+                                         uint32_t ebytes)
+{
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const uint32_t x = __byte_perm(w[i], 0, 0x4440 + p);  // byte p, zero extended
+            const uint32_t v = lds_u32(x * ebytes + tab_j_lane);  // IMAD (fma pipe)
+            if (kFirst) acc[4 * i + p] = v;
+            else acc[4 * i + p] ^= v;
+        }
+    }
+}
+
+// One 16-byte column of one stripe: load K sources, look up, transpose -> r[row] (uint4).
+//   sp        : address of column `col` of source 0 (uniform modes) / of shard 0 (plan mode)
+//   kPlan     : source j at sp + src_off[j] (smem) instead of sp + j*stride
+template <int K, bool kPlan>
+__device__ __forceinline__ void column_rows(const uint8_t *sp, uint32_t stride, uint32_t k_rt,
+                                            const uint32_t *src_off, uint32_t tab_lane,
+                                            uint32_t log2R, uint32_t tail_bytes, uint4 (&r)[4])
+{
+    uint32_t acc[16];
+    const uint32_t xshift = 4u << log2R;         // byte offset of entry x = x * 4R
+    const uint32_t tstride = 1024u << log2R;    // bytes per source table
+    if (K > 0) {
+        uint4 d[K > 0 ? K : 1];
+#pragma unroll
+        for (int j = 0; j < K; j++)
+            d[j] = ldg_stream(sp + (kPlan ? src_off[j] : (uint32_t)j * stride));
+        if (tail_bytes) {
+#pragma unroll
+            for (int j = 0; j < K; j++) d[j] = mask_tail(d[j], tail_bytes);
+        }
+        lookup16<true>(acc, d[0], tab_lane, xshift);
+#pragma unroll
+        for (int j = 1; j < K; j++) lookup16<false>(acc, d[j], tab_lane + j * tstride, xshift);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+        for (uint32_t j0 = 0; j0 < k_rt; j0 += 4) {
+            uint4 d[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t j = j0 + u;
+                d[u] = make_uint4(0, 0, 0, 0);
+                if (j < k_rt) {
+                    d[u] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
+                    if (tail_bytes) d[u] = mask_tail(d[u], tail_bytes);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (j0 + u < k_rt) lookup16<false>(acc, d[u], tab_lane + (j0 + u) * tstride, xshift);
+        }
+    }
+    uint32_t o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        transpose4x4(acc[4 * i + 0], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3], o[0][i], o[1][i],
+                     o[2][i], o[3][i]);
+#pragma unroll
+    for (int row = 0; row < 4; row++) r[row] = make_uint4(o[row][0], o[row][1], o[row][2], o[row][3]);
+}
+
+// ------------------------------------------------------------------ the streaming kernel
+template <int K, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_constant__ ApplyParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemLayout L = carve(smem_raw, p.k, p.log2R);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t k = (K > 0) ? (uint32_t)K : p.k;
+
+    for (uint32_t i = tid; i < 512; i += kThreads) L.gf_exp[i] = c_gf_exp[i];
+    for (uint32_t i = tid; i < 256; i += kThreads) L.gf_log[i] = c_gf_log[i];
+    __syncthreads();
+
+    const uint32_t R = 1u << p.log2R;
+    const uint32_t tab_lane =
+        (uint32_t)__cvta_generic_to_shared(L.tab) + ((lane & (R - 1)) << 2);
+
+    if (MODE != kModePlan) {
+        // ---- uniform coefficient matrix: build once, then warps stream items ----------------
+        build_tables(L, p.coef, k, k, p.rows, p.log2R);
+        __syncthreads();
+
+        const uint32_t ips = p.items_per_stripe;
+        const uint32_t total = p.n * ips;  // host guarantees < 2^32
+        const uint32_t gwarps = gridDim.x * (kThreads / 32);
+        for (uint32_t item = blockIdx.x * (kThreads / 32) + warp; item < total; item += gwarps) {
+            const uint32_t s = item / ips;
+            const uint32_t c = item - s * ips;
+            const uint32_t len = p.shard_len ? __ldg(p.shard_len + s) : p.stride;
+            const uint32_t nvec = (len + 15) >> 4;
+            const uint32_t col = c * 32 + lane;
+            uint32_t mm = 0;
+            if (col < nvec) {
+                const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
+                const uint8_t *sp = p.src + (unsigned long long)s * p.src_pitch + (size_t)col * 16;
+                uint4 r[4];
+                column_rows<K, false>(sp, p.stride, k, nullptr, tab_lane, p.log2R, tail, r);
+                if (MODE == kModeEncode) {
+                    uint8_t *dp = p.dst + (unsigned long long)s * p.dst_pitch + (size_t)col * 16;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < (int)p.rows) stg_stream(dp + (size_t)i * p.stride, r[i]);
+                } else {
+                    // stored parity rows follow the k data shards of the same stripe
+                    const uint8_t *pp = sp + (size_t)(k + p.row_off) * p.stride;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (i < (int)p.rows) {
+                            uint4 st = ldg_stream(pp + (size_t)i * p.stride);
+                            if (tail) st = mask_tail(st, tail);
+                            const uint32_t diff = (st.x ^ r[i].x) | (st.y ^ r[i].y) |
+                                                  (st.z ^ r[i].z) | (st.w ^ r[i].w);
+                            if (diff) mm |= 1u << (p.row_off + i);
+                        }
+                    }
+                }
+            }
+            if (MODE == kModeVerify) {
+                // warp-shuffle OR reduction of the per-lane mismatch bits, one atomic per warp
+                mm = __reduce_or_sync(0xffffffffu, mm);
+                if (mm && lane == 0) atomicOr(p.mismatch + s, mm);
+            }
+        }
+    } else {
+        // ---- per-stripe matrices: CTAs pull stripes from an atomic counter -------------------
+        unsigned long long prev_present = ~0ull, prev_out = ~0ull;
+        bool have_tables = false;
+        for (;;) {
+            __syncthreads();  // previous stripe's tables / offsets no longer in use
+            if (tid == 0) *L.sched = atomicAdd(p.counter, 1u);
+            __syncthreads();
+            const uint32_t s = *L.sched;
+            if (s >= p.n) break;
+            const StripePlan *pl = p.plan + s;
+            const int nrows_total = pl->nrows;
+            const int rows = min(kRowsPerPass, nrows_total - (int)p.row_off);
+            if (pl->unrecoverable || rows <= 0) continue;
+            const unsigned long long kp = pl->key_present, ko = pl->key_out;
+            if (!(have_tables && kp == prev_present && ko == prev_out)) {
+                if (tid < k) L.src_off[tid] = (uint32_t)pl->surv[tid] * p.stride;
+                if (tid < (uint32_t)rows) L.dst_off[tid] = (uint32_t)pl->out_idx[p.row_off + tid] * p.stride;
+                for (uint32_t e = tid; e < (uint32_t)rows * kMaxK; e += kThreads)
+                    L.coef[e] = pl->coef[p.row_off + e / kMaxK][e % kMaxK];
+                __syncthreads();
+                build_tables(L, L.coef, kMaxK, k, (uint32_t)rows, p.log2R);
+                __syncthreads();
+                prev_present = kp;
+                prev_out = ko;
+                have_tables = true;
+            }
+            const uint32_t len = p.shard_len ? __ldg(p.shard_len + s) : p.stride;
+            const uint32_t nvec = (len + 15) >> 4;
+            const uint8_t *sbase = p.src + (unsigned long long)s * p.src_pitch;
+            uint8_t *dbase = p.dst + (unsigned long long)s * p.dst_pitch;
+            for (uint32_t col = tid; col < nvec; col += kThreads) {
+                const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
+                uint4 r[4];
+                column_rows<K, true>(sbase + (size_t)col * 16, p.stride, k, L.src_off, tab_lane,
+                                     p.log2R, tail, r);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (i < rows) stg_stream(dbase + L.dst_off[i] + (size_t)col * 16, r[i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ decode planning
+struct PlanParams {
+    const uint8_t *present;  // n*(k+m)
+    const uint8_t *want;     // nullable
+    int32_t *status;         // nullable, n
+    StripePlan *plan;        // n
+    uint32_t *counter;       // reset to 0 for the apply kernel's scheduler
+    uint32_t n, k, m;
+    uint8_t P[kMaxM * kMaxK];  // parity rows, P[i*k + j]
+};
+
+constexpr int kPlanWarps = 4;
+
+// One warp per stripe: pick the first k present shards, invert the k x k submatrix of
+// [I;P] they form (Gauss-Jordan, lanes own columns), compose the rows that map the
+// survivors straight to every wanted absent shard.
+__global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_constant__ PlanParams q)
+{
+    __shared__ uint8_t s_exp[512];
+    __shared__ uint8_t s_log[256];
+    __shared__ uint8_t s_A[kPlanWarps][kMaxK][2 * kMaxK];
+    __shared__ uint8_t s_surv[kPlanWarps][kMaxK];
+    __shared__ uint8_t s_out[kPlanWarps][kMaxM];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < 512; i += blockDim.x) s_exp[i] = c_gf_exp[i];
+    for (uint32_t i = tid; i < 256; i += blockDim.x) s_log[i] = c_gf_log[i];
+    if (blockIdx.x == 0 && tid == 0) *q.counter = 0;
+    __syncthreads();
+    auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
+        return (a && b) ? s_exp[s_log[a] + s_log[b]] : 0u;
+    };
+
+    const uint32_t s = blockIdx.x * kPlanWarps + warp;
+    if (s >= q.n) return;
+    const uint32_t k = q.k, m = q.m, tot = k + m;
+    StripePlan *pl = q.plan + s;
+    const uint8_t *pr = q.present + (size_t)s * tot;
+    const uint8_t *wn = q.want ? q.want + (size_t)s * tot : nullptr;
+
+    // presence / wanted masks (tot <= 40: two ballot rounds)
+    const bool p0 = lane < tot && pr[lane] != 0;
+    const bool p1 = lane + 32 < tot && pr[lane + 32] != 0;
+    const unsigned long long present =
+        (unsigned long long)__ballot_sync(0xffffffffu, p0) |
+        ((unsigned long long)__ballot_sync(0xffffffffu, p1) << 32);
+    const bool w0 = lane < tot && !p0 && (!wn || wn[lane] != 0);
+    const bool w1 = lane + 32 < tot && !p1 && (!wn || wn[lane + 32] != 0);
+    unsigned long long outmask = (unsigned long long)__ballot_sync(0xffffffffu, w0) |
+                                 ((unsigned long long)__ballot_sync(0xffffffffu, w1) << 32);
+    const int npresent = __popcll(present);
+    const bool bad = npresent < (int)k;
+    if (bad) outmask = 0;
+    int nrows = __popcll(outmask);
+
+    if (lane == 0) {
+        // survivors: first k present; outputs: wanted absent shards in index order
+        unsigned long long pm = present;
+        for (uint32_t r = 0; r < k && pm; r++) {
+            const int i = __ffsll((long long)pm) - 1;
+            s_surv[warp][r] = (uint8_t)i;
+            pm &= pm - 1;
+        }
+        unsigned long long om = outmask;
+        for (int r = 0; r < nrows; r++) {
+            const int i = __ffsll((long long)om) - 1;
+            s_out[warp][r] = (uint8_t)i;
+            om &= om - 1;
+        }
+        pl->key_present = present;
+        pl->key_out = outmask;
+        pl->nrows = (uint8_t)nrows;
+        pl->unrecoverable = bad ? 1 : 0;
+        if (q.status) q.status[s] = bad ? -4 : 0;
+    }
+    __syncwarp();
+    if (bad || nrows == 0) return;
+
+    // A = [S | I], S[r][c] = generator row surv[r]
+    uint8_t(*A)[2 * kMaxK] = s_A[warp];
+    for (uint32_t r = 0; r < k; r++) {
+        const uint32_t g = s_surv[warp][r];
+        for (uint32_t c = lane; c < 2 * k; c += 32) {
+            uint8_t v;
+            if (c < k) v = g < k ? (uint8_t)(g == c) : q.P[(g - k) * k + c];
+            else v = (uint8_t)(c - k == r);
+            A[r][c] = v;
+        }
+    }
+    __syncwarp();
+    for (uint32_t c = 0; c < k; c++) {
+        // pivot search: lanes are rows
+        const bool cand = lane < k && lane >= c && A[lane][c] != 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, cand);
+        if (!bal) {  // singular: cannot happen for an MDS generator; report unrecoverable
+            if (lane == 0) {
+                pl->nrows = 0;
+                pl->unrecoverable = 1;
+                if (q.status) q.status[s] = -4;
+            }
+            return;
+        }
+        const uint32_t piv = __ffs(bal) - 1;
+        const uint32_t iv = s_exp[255 - s_log[A[piv][c]]];
+        __syncwarp();
+        for (uint32_t x = lane; x < 2 * k; x += 32) {
+            const uint8_t a = A[piv][x], b = A[c][x];
+            A[piv][x] = b;                   // swap (no-op when piv == c)
+            A[c][x] = (uint8_t)mul(a, iv);   // scaled pivot row
+        }
+        __syncwarp();
+        for (uint32_t r = 0; r < k; r++) {
+            if (r == c) continue;
+            const uint32_t f = A[r][c];
+            __syncwarp();
+            if (f)
+                for (uint32_t x = lane; x < 2 * k; x += 32) A[r][x] ^= (uint8_t)mul(f, A[c][x]);
+            __syncwarp();
+        }
+    }
+    // inverse now in A[:, k..2k).  Compose rows for the outputs.
+    for (int r = 0; r < nrows; r++) {
+        const uint32_t o = s_out[warp][r];
+        if (lane < k) {
+            uint32_t v;
+            if (o < k) {
+                v = A[o][k + lane];
+            } else {
+                v = 0;
+                for (uint32_t x = 0; x < k; x++) v ^= mul(q.P[(o - k) * k + x], A[x][k + lane]);
+            }
+            pl->coef[r][lane] = (uint8_t)v;
+        }
+    }
+    if (lane < k) pl->surv[lane] = s_surv[warp][lane];
+    if (lane < (uint32_t)nrows) pl->out_idx[lane] = s_out[warp][lane];
+}
+
+// ------------------------------------------------------------------ synthetic data
+// splitmix64 counter stream of SURVEY.md 8(d) (the CPU checker generates the same stream).
+__global__ void fill_random_kernel(unsigned long long *dst, size_t nwords, unsigned long long seed,
+                                   unsigned long long first_idx)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords;
+         i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + (first_idx + i + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        dst[i] = z ^ (z >> 31);
+    }
+}
+
+}  // namespace garage_ec

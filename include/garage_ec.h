@@ -1,0 +1,170 @@
+/*
+ * garage_ec.h -- C ABI of libgarage_ec.so: the B200 (sm_100a) erasure-coding block path
+ * for Garage.
+ *
+ * The reference (deuxfleurs-org/garage v1.2.0) has no FFI and no erasure coding; its
+ * drop-in boundary is the Rust surface of garage_block::manager::BlockManager
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference call site whose
+ * CPU-side per-block work it replaces; the Rust `src/block/cuda` shim that binds these
+ * symbols is shown in INTEGRATION.md.
+ *
+ * Conventions (mirroring the reference's):
+ *   errors     every call returns 0 or a negative GARAGE_EC_E_* code; nothing aborts or
+ *              throws across the boundary (reference: Result<_, garage_util::error::Error>,
+ *              src/util/error.rs:14-82; Rust maps non-zero to Error::Message /
+ *              Error::CorruptData so resync's backoff handles it, src/block/resync.rs:300-315).
+ *   ownership  caller owns every buffer; the library keeps no pointer after a HOST call
+ *              returns, or after the stream work of a DEVICE call completes
+ *              (reference: bytes::Bytes, immutable + refcounted).
+ *   threading  a context may be used from many OS threads at once (reference: tokio
+ *              spawn_blocking, src/block/block.rs:86, src/api/s3/put.rs:419,446).
+ *   no CPU fallback: if there is no usable CUDA device, garage_ec_create fails with
+ *              GARAGE_EC_E_NODEVICE.
+ *
+ * Arithmetic (normative definition in DESIGN.md; CPU oracle under oracle/):
+ *   GF(2^8), polynomial 0x11D, alpha = 2.  One stripe = one block (post-compression bytes
+ *   of DataBlock::from_buffer, src/block/block.rs:85-96).  shard_len = ceil(block_len/k);
+ *   data shard j = block bytes [j*shard_len,(j+1)*shard_len) zero-padded; parity row
+ *   i = XOR_j P[i][j] * data[j].
+ *
+ * Batch geometry ("shard layout"), shared by encode / reconstruct / verify:
+ *   stride      bytes between consecutive shards; multiple of 16; >= every shard_len[s];
+ *               (k+m)*stride < 4 GiB
+ *   shard_len   per-stripe valid bytes per shard (NULL = `stride` for every stripe).
+ *               Bytes in [shard_len, roundup16(shard_len)) of every OUTPUT shard are
+ *               written as zero; input bytes there are ignored.  Beyond roundup16 nothing
+ *               is read or written.
+ *   all base pointers 16-byte aligned.
+ */
+#ifndef GARAGE_EC_H
+#define GARAGE_EC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GARAGE_EC_ABI_VERSION 1
+
+/* error codes */
+#define GARAGE_EC_OK 0
+#define GARAGE_EC_E_INVALID (-1)       /* bad argument / geometry */
+#define GARAGE_EC_E_CUDA (-2)          /* CUDA runtime error, see garage_ec_last_error */
+#define GARAGE_EC_E_NOMEM (-3)         /* host or device allocation failed */
+#define GARAGE_EC_E_UNRECOVERABLE (-4) /* >= 1 stripe had < k shards; see status[] */
+#define GARAGE_EC_E_NODEVICE (-5)      /* no CUDA device / wrong architecture */
+#define GARAGE_EC_E_ALIGN (-6)         /* pointer or stride alignment violated */
+
+/* matrix kinds */
+#define GARAGE_EC_VANDERMONDE 0 /* systematic Vandermonde (default), G = V * inv(V[0..k)) */
+#define GARAGE_EC_CAUCHY 1      /* P[i][j] = 1/((k+i) xor j) */
+
+/* where the caller's buffers live */
+#define GARAGE_EC_MEM_HOST 0   /* all pointers host; call is synchronous */
+#define GARAGE_EC_MEM_DEVICE 1 /* all pointers device (this ctx's GPU); call enqueues on `stream` */
+
+/* limits of this build */
+#define GARAGE_EC_MAX_K 32
+#define GARAGE_EC_MAX_M 8
+
+typedef struct garage_ec_ctx garage_ec_ctx;
+
+/* ---- lifecycle -------------------------------------------------------------------------
+ * One context per (GPU, k, m, matrix).  Replaces nothing in the reference: it is the state
+ * a BlockManager built with `erasure_coding = {data_shards, parity_shards}` would hold
+ * next to `data_layout` (src/block/manager.rs:122-192).                                    */
+int garage_ec_create(garage_ec_ctx **out, int cuda_device, int k, int m, int matrix_kind);
+/* same, with an explicit m x k parity matrix (row-major) -- used by non-zero ranks after
+ * the NCCL broadcast of rank 0's matrix.                          */
+int garage_ec_create_with_matrix(garage_ec_ctx **out, int cuda_device, int k, int m,
+                                 const uint8_t *parity_rows);
+void garage_ec_destroy(garage_ec_ctx *ctx);
+
+int garage_ec_matrix(const garage_ec_ctx *ctx, uint8_t *out_m_by_k); /* parity rows, row-major */
+int garage_ec_params(const garage_ec_ctx *ctx, int *k, int *m, int *cuda_device);
+const char *garage_ec_strerror(int code);
+/* detail of the last GARAGE_EC_E_CUDA on this context (thread-unsafe snapshot; "" if none) */
+const char *garage_ec_last_error(const garage_ec_ctx *ctx);
+int garage_ec_abi_version(void);
+
+/* ---- geometry helpers ------------------------------------------------------------------ */
+uint32_t garage_ec_shard_len(uint32_t block_len, int k); /* ceil(block_len / k)            */
+size_t garage_ec_stride_for(uint32_t shard_len);         /* shard_len rounded up to 128 B   */
+
+/* ---- ENCODE -- call site: BlockManager::rpc_put_block, src/block/manager.rs:366-408,
+ * right after DataBlock::from_buffer (manager.rs:376): the k data shards of each block go in,
+ * the m parity shards come out; shard i is then sent to node i of the (k+m)-node set.
+ *   data   : n * k * stride bytes, shard j of stripe s at (s*k + j) * stride
+ *   parity : n * m * stride bytes, row  i of stripe s at (s*m + i) * stride                */
+int garage_ec_encode(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
+                     const uint32_t *shard_len, size_t stride, size_t n_stripes, int mem_kind,
+                     void *cuda_stream);
+
+/* ---- RECONSTRUCT -- call sites: BlockManager::rpc_get_raw_block_internal,
+ * src/block/manager.rs:276-339 (GET: any k of k+m shards arrived, rebuild the missing data
+ * shards) and BlockResyncManager::resync_block fetch branch, src/block/resync.rs:460-500
+ * (repair: rebuild this node's own shard from k survivors).
+ *   shards  : n * (k+m) * stride bytes, shard i of stripe s at (s*(k+m) + i) * stride
+ *   present : n * (k+m) bytes in {0,1}
+ *   want    : NULL = rebuild every absent shard; else n*(k+m) bytes, only absent shards
+ *             with want != 0 are rebuilt (GET wants data shards only; resync wants one)
+ *   status  : n int32: 0 ok, GARAGE_EC_E_UNRECOVERABLE if < k present (stripe untouched)
+ * Survivors used: the first k present shards in index order.  HOST calls return
+ * GARAGE_EC_E_UNRECOVERABLE if any stripe was; DEVICE calls only fill status[].            */
+int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
+                          const uint8_t *want, int32_t *status, const uint32_t *shard_len,
+                          size_t stride, size_t n_stripes, int mem_kind, void *cuda_stream);
+
+/* ---- VERIFY (scrub) -- call sites: DataBlock::verify via BlockManager::read_block,
+ * src/block/manager.rs:554-609 / src/block/block.rs:69-83, driven by ScrubWorker::work,
+ * src/block/repair.rs:438-490: recompute parity from the k data shards and compare with
+ * the stored parity.  mismatch[s] bit i set iff parity row i differs.                      */
+int garage_ec_verify(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismatch,
+                     const uint32_t *shard_len, size_t stride, size_t n_stripes, int mem_kind,
+                     void *cuda_stream);
+
+/* ---- BLOCK-LEVEL convenience (host memory only) -----------------------------------------
+ * What rpc_put_block hands over is a contiguous block (bytes::Bytes), not shards.  These do
+ * the framing (split + zero pad, src/api/s3/put.rs:583-617 block sizes) on the way to the
+ * GPU so the Rust side needs no extra copy.
+ *   blocks[s]     : block_len[s] bytes (host)
+ *   parity_out    : n * m * stride bytes (host), row i of block s at (s*m + i) * stride.
+ *                   The k data shards are just the slices block[j*L .. (j+1)*L) with
+ *                   L = garage_ec_shard_len(block_len, k) (zero padded), so they never
+ *                   cross PCIe back: Rust sends those slices of the original Bytes.
+ *   stride        : >= garage_ec_shard_len(max block_len, k), multiple of 16               */
+int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks,
+                            const uint32_t *block_len, size_t n_blocks, uint8_t *parity_out,
+                            size_t stride);
+/* inverse for GET: shards (host, shard layout) + present -> blocks_out[s] (block_len[s]
+ * bytes each).  Runs reconstruct only for stripes with an absent data shard.               */
+int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *present,
+                            const uint32_t *block_len, size_t n_blocks, size_t stride,
+                            uint8_t *const *blocks_out, int32_t *status);
+
+/* ---- utilities used by the harness ------------------------------------------------------
+ * device-side synthetic data (same splitmix64 counter stream as the oracle's
+ * generator): fills dst[0..len) (device) with stream bytes at `offset`
+ * (len, offset multiples of 8).                                                            */
+int garage_ec_fill_random(garage_ec_ctx *ctx, uint8_t *dst_device, size_t len, uint64_t seed,
+                          uint64_t offset, void *cuda_stream);
+/* pinned host memory for block / shard buffers: the Rust side lands the HTTP body copy
+ * (BytesBuf::take_exact, src/net/bytes_buf.rs:66-117) directly in such a buffer so the DMA
+ * engines can read it.  Pageable memory is accepted everywhere, only slower.               */
+int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes);
+void garage_ec_host_free(garage_ec_ctx *ctx, void *ptr);
+
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches)        */
+uint64_t garage_ec_launch_count(const garage_ec_ctx *ctx);
+/* per-kernel CUDA-event timing of the RS kernels (encode / reconstruct / verify main
+ * kernel, recorded on the stream they were launched on).  garage_ec_timing_read waits for
+ * the recorded kernels, adds their durations to *total_ms / *launches and resets.          */
+int garage_ec_set_timing(garage_ec_ctx *ctx, int enabled);
+int garage_ec_timing_read(garage_ec_ctx *ctx, double *total_ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GARAGE_EC_H */
