@@ -34,7 +34,7 @@ GIB = float(1 << 30)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--k", type=int, default=10)
@@ -108,7 +108,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.err = repr(e)
                 break
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.nv:
