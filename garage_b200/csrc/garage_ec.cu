@@ -43,7 +43,6 @@ struct garage_ec_ctx {
     uint8_t P[kMaxM * kMaxK] = {0};
     int sm_count = 0;
     size_t smem_optin = 0;
-    int log2R = 0;
     size_t smem_bytes = 0;
     std::mutex host_mu;  // serialises HOST-mode calls (they share the lanes)
     HostLane lanes[kHostLanes];
@@ -171,7 +170,7 @@ int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pit
             p.rows = (uint32_t)(ctx->m - r0 < kRowsPerPass ? ctx->m - r0 : kRowsPerPass);
             p.row_off = (uint32_t)r0;
             p.items_per_stripe = ips;
-            p.log2R = (uint32_t)ctx->log2R;
+            p.row_bytes = 128;
             for (uint32_t i = 0; i < p.rows; i++)
                 memcpy(p.coef + i * ctx->k, ctx->P + (r0 + i) * ctx->k, ctx->k);
             cudaError_t e = mode == kModeEncode ? launch_apply<kModeEncode>(ctx, p, st)
@@ -223,7 +222,7 @@ int run_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
         p.n = (uint32_t)n;
         p.k = (uint32_t)ctx->k;
         p.row_off = (uint32_t)r0;
-        p.log2R = (uint32_t)ctx->log2R;
+        p.row_bytes = 128;
         e = launch_apply<kModePlan>(ctx, p, st);
         if (e != cudaSuccess) return set_cuda_error(ctx, e, "rs_apply_kernel<plan> launch");
     }
@@ -282,17 +281,11 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    ctx->log2R = -1;
-    for (int l = 5; l >= 0; l--)
-        if (smem_bytes_for(k, l) <= ctx->smem_optin) {
-            ctx->log2R = l;
-            break;
-        }
-    if (ctx->log2R < 0) {
+    ctx->smem_bytes = smem_bytes_for(k);
+    if (ctx->smem_bytes > ctx->smem_optin) {
         delete ctx;
-        return GARAGE_EC_E_INVALID;
+        return GARAGE_EC_E_NODEVICE;
     }
-    ctx->smem_bytes = smem_bytes_for(k, ctx->log2R);
     if (cudaSetDevice(device) != cudaSuccess) {
         delete ctx;
         return GARAGE_EC_E_NODEVICE;

@@ -1,6 +1,6 @@
 // rs_kernels.cuh -- sm_100a kernels of the Garage erasure-coding block path.
 //
-// What they compute (normative definition: DESIGN.md "Arithmetic", oracle/rs_oracle.h):
+// What they compute (normative definition: DESIGN.md "Arithmetic"):
 //     out[i][t] = XOR_j C[i][j] * src[j][t]         over GF(2^8)/0x11D, byte-wise
 // for rows i of a small coefficient matrix C (the parity rows P for encode/verify, a
 // per-stripe composed decode matrix for reconstruct) and the k source shards of a stripe.
@@ -9,20 +9,27 @@
 // BlockResyncManager::resync_block (src/block/resync.rs:460-500), DataBlock::verify /
 // ScrubWorker::work (src/block/block.rs:69-83, src/block/repair.rs:438-490).
 //
-// Design (DESIGN.md "Kernel"):
+// Design (DESIGN.md "Kernels"):
 //  * HBM-bound byte work, no tensor cores.  The per-byte GF multiply-accumulate for up to 4
 //    output rows is ONE shared-memory lookup: T_j[x] = {C0j*x, C1j*x, C2j*x, C3j*x} packed in
 //    a 32-bit word, so a data byte costs one LDS + one XOR for all four rows.
-//  * Random byte indices would bank-conflict ~3.5-way on a plain 256-word table.  Each table
-//    is therefore replicated R times with replica g = lane % R living in banks
-//    {g, g+R, ...}: word address = (j*256 + x)*R + g.  R = 16 (k <= 13): two lanes share two
-//    banks -> 1.5 wavefronts/LDS expected; R = 32 (k <= 6): lane-private banks, conflict-free.
+//  * Conflict-free lookups at 16 KB per table ("sub-warp interleaving").  Random byte indices
+//    into a plain 256-word table serialise ~3.5-way, lane-private replicas (32 KB/table) do
+//    not fit k = 10.  Instead G = 32/R tables share one 32 KB "group": table j = G*t + sub is
+//    replicated R times in banks [sub*R, sub*R + R) (word t*8192 + x*32 + sub*R + g).  The
+//    warp is cut in G sub-warps of R lanes; at any lookup instruction sub-warp q works on
+//    source G*t + (phase xor q), i.e. every sub-warp is in a different table of the group and
+//    every lane owns its bank: word = t*8192 + x*32 + (lane xor phase*R).  The source order is
+//    simply permuted per sub-warp when the data is LOADED (slot u holds source u xor q), which
+//    costs nothing because XOR-accumulation commutes.  RS(10,4): G = 2, 5 groups = 160 KB,
+//    1.0 wavefronts per LDS (the first version, plain R = 16 replication, measured 2.07).
 //  * log/antilog tables sit in __constant__ memory and are copied to shared memory; they are
 //    only used to BUILD the product tables (once per launch for encode/verify, once per
 //    change of erasure pattern for reconstruct), never in the streaming loop.
 //  * Streaming loop: one 16-byte column of all k shards per thread (coalesced 512 B per warp
 //    per shard, ld.global.nc.L1::no_allocate.v4), 16 lookups per shard, 4x4 byte transposes
-//    with PRMT, one 16-byte st.global.cs per output row.
+//    with PRMT, one 16-byte st.global.cs per output row; the next column's vectors are
+//    prefetched into registers while the current one is processed.
 //  * Persistent grid: one CTA per SM (tables fill shared memory), work items handed to warps
 //    (encode/verify) or to CTAs through an atomic counter (reconstruct).
 #pragma once
@@ -33,10 +40,27 @@
 
 namespace garage_ec {
 
-constexpr int kThreads = 512;  // threads per CTA (16 warps); 1 CTA per SM
+#ifndef GEC_THREADS
+#define GEC_THREADS 512
+#endif
+#ifndef GEC_PIPELINE
+#define GEC_PIPELINE 1  // prefetch the next column's k vectors into registers while computing
+#endif
+constexpr int kThreads = GEC_THREADS;  // threads per CTA; 1 CTA per SM (tables fill smem)
 constexpr int kMaxK = 32;
 constexpr int kMaxM = 8;
 constexpr int kRowsPerPass = 4;  // output rows packed in one 32-bit table word
+constexpr uint32_t kGroupBytes = 32768;  // one table group: 256 rows x 32 banks x 4 B
+
+// tables per 32 KB group for k sources: smallest G (least padding) whose groups fit 227 KB
+__host__ __device__ constexpr int log2_group_for_k(int k)
+{
+    return k <= 7 ? 0 : (k <= 14 ? 1 : (k <= 28 ? 2 : 3));
+}
+__host__ __device__ constexpr int slots_for_k(int k)
+{
+    return ((k + (1 << log2_group_for_k(k)) - 1) >> log2_group_for_k(k)) << log2_group_for_k(k);
+}
 
 __constant__ uint8_t c_gf_exp[512] = GARAGE_EC_GF_EXP_INIT;
 __constant__ uint8_t c_gf_log[256] = GARAGE_EC_GF_LOG_INIT;
@@ -70,7 +94,7 @@ struct ApplyParams {
     uint32_t rows;              // outputs this pass (<= 4), uniform modes
     uint32_t row_off;           // first output row of this pass
     uint32_t items_per_stripe;  // ceil(ceil(stride/16)/32), uniform modes
-    uint32_t log2R;             // table replication
+    uint32_t row_bytes;         // 128: bytes per table row (a register operand keeps x*128 an IMAD)
     uint8_t coef[kRowsPerPass * kMaxK];  // uniform modes: coef[i*k + j]
 };
 
@@ -126,8 +150,8 @@ __device__ __forceinline__ void transpose4x4(const uint32_t a0, const uint32_t a
 
 // ------------------------------------------------------------------ shared memory carve-up
 struct SmemLayout {
-    // dynamic smem: [tables: k*256*R words][exp 512][log 256][src_off 32 u32][dst_off 4 u32]
-    //               [coef 4*32][sched 1 u32]
+    // dynamic smem: [table groups: ceil(k/G) * 32 KB][exp 512][log 256][src_off 32 u32]
+    //               [dst_off 4 u32][coef 4*32][sched 1 u32]
     uint32_t *tab;
     uint8_t *gf_exp;
     uint8_t *gf_log;
@@ -137,16 +161,16 @@ struct SmemLayout {
     uint32_t *sched;
 };
 constexpr size_t kSmemAux = 512 + 256 + kMaxK * 4 + kRowsPerPass * 4 + kRowsPerPass * kMaxK + 16;
-__host__ __device__ inline size_t smem_bytes_for(int k, int log2R)
+__host__ __device__ inline size_t smem_bytes_for(int k)
 {
-    return (size_t)k * 256 * 4 * ((size_t)1 << log2R) + kSmemAux;
+    return (size_t)(slots_for_k(k) >> log2_group_for_k(k)) * kGroupBytes + kSmemAux;
 }
 
-__device__ __forceinline__ SmemLayout carve(unsigned char *base, uint32_t k, uint32_t log2R)
+__device__ __forceinline__ SmemLayout carve(unsigned char *base, uint32_t k)
 {
     SmemLayout L;
     L.tab = reinterpret_cast<uint32_t *>(base);
-    unsigned char *p = base + ((size_t)k * 256 * 4 << log2R);
+    unsigned char *p = base + (size_t)(slots_for_k((int)k) >> log2_group_for_k((int)k)) * kGroupBytes;
     L.gf_exp = p;
     p += 512;
     L.gf_log = p;
@@ -161,16 +185,18 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, uint32_t k, uin
     return L;
 }
 
-// Build the replicated product tables for `rows` (<=4) coefficient rows coef[i*cstride + j].
-// Caller syncs before (old tables idle, coef visible) and after.
+// Build the product tables for `rows` (<=4) coefficient rows coef[i*cstride + j], j < k; the
+// padding tables of a partial last group are all zero.  Caller syncs before and after.
 __device__ __forceinline__ void build_tables(const SmemLayout &L, const uint8_t *coef, uint32_t cstride,
-                                             uint32_t k, uint32_t rows, uint32_t log2R)
+                                             uint32_t k, uint32_t rows)
 {
-    const uint32_t R = 1u << log2R;
-    for (uint32_t e = threadIdx.x; e < k * 256; e += kThreads) {
+    const uint32_t lg = (uint32_t)log2_group_for_k((int)k);
+    const uint32_t slots = (uint32_t)slots_for_k((int)k);
+    const uint32_t R = 32u >> lg;  // replicas per table = lanes per sub-warp (>= 4)
+    for (uint32_t e = threadIdx.x; e < slots * 256; e += kThreads) {
         const uint32_t j = e >> 8, x = e & 255;
         uint32_t w = 0;
-        if (x) {
+        if (x && j < k) {
             const uint32_t lx = L.gf_log[x];
 #pragma unroll
             for (uint32_t i = 0; i < kRowsPerPass; i++) {
@@ -180,76 +206,34 @@ __device__ __forceinline__ void build_tables(const SmemLayout &L, const uint8_t 
                 }
             }
         }
-        uint32_t *dst = L.tab + ((size_t)e << log2R);
-        if (R >= 4) {
-            const uint4 v = make_uint4(w, w, w, w);
-            for (uint32_t g = 0; g < R; g += 4) *reinterpret_cast<uint4 *>(dst + g) = v;
-        } else {
-            for (uint32_t g = 0; g < R; g++) dst[g] = w;
-        }
+        // table j: group t = j >> lg, banks [sub*R, sub*R + R), row x
+        uint32_t *dst = L.tab + (size_t)(j >> lg) * (kGroupBytes / 4) + x * 32 + (j & ((1u << lg) - 1)) * R;
+        const uint4 v = make_uint4(w, w, w, w);
+        for (uint32_t g = 0; g < R; g += 4) *reinterpret_cast<uint4 *>(dst + g) = v;
     }
 }
 
-// 16 table lookups for one 16-byte vector of source j; acc[4*w + p] ^= T_j[byte p of word w]
+// 16 table lookups for one 16-byte vector; acc[4*w + p] ^= T[byte p of word w]
+//   base = shared address of (group, this lane's bank for this phase); row_bytes = 128
 template <bool kFirst>
-__device__ __forceinline__ void lookup16(uint32_t (&acc)[16], const uint4 &d, uint32_t tab_j_lane,
-                                         uint32_t ebytes)
+__device__ __forceinline__ void lookup16(uint32_t (&acc)[16], const uint4 &d, uint32_t base,
+                                         uint32_t row_bytes)
 {
     const uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            const uint32_t x = __byte_perm(w[i], 0, 0x4440 + p);  // byte p, zero extended
-            const uint32_t v = lds_u32(x * ebytes + tab_j_lane);  // IMAD (fma pipe)
+            const uint32_t x = __byte_perm(w[i], 0, 0x4440 + p);  // byte p, zero extended (alu pipe)
+            const uint32_t v = lds_u32(x * row_bytes + base);     // IMAD (fma pipe)
             if (kFirst) acc[4 * i + p] = v;
             else acc[4 * i + p] ^= v;
         }
     }
 }
 
-// One 16-byte column of one stripe: load K sources, look up, transpose -> r[row] (uint4).
-//   sp        : address of column `col` of source 0 (uniform modes) / of shard 0 (plan mode)
-//   kPlan     : source j at sp + src_off[j] (smem) instead of sp + j*stride
-template <int K, bool kPlan>
-__device__ __forceinline__ void column_rows(const uint8_t *sp, uint32_t stride, uint32_t k_rt,
-                                            const uint32_t *src_off, uint32_t tab_lane,
-                                            uint32_t log2R, uint32_t tail_bytes, uint4 (&r)[4])
+__device__ __forceinline__ void rows_from_acc(const uint32_t (&acc)[16], uint4 (&r)[4])
 {
-    uint32_t acc[16];
-    const uint32_t xshift = 4u << log2R;         // byte offset of entry x = x * 4R
-    const uint32_t tstride = 1024u << log2R;    // bytes per source table
-    if (K > 0) {
-        uint4 d[K > 0 ? K : 1];
-#pragma unroll
-        for (int j = 0; j < K; j++)
-            d[j] = ldg_stream(sp + (kPlan ? src_off[j] : (uint32_t)j * stride));
-        if (tail_bytes) {
-#pragma unroll
-            for (int j = 0; j < K; j++) d[j] = mask_tail(d[j], tail_bytes);
-        }
-        lookup16<true>(acc, d[0], tab_lane, xshift);
-#pragma unroll
-        for (int j = 1; j < K; j++) lookup16<false>(acc, d[j], tab_lane + j * tstride, xshift);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; i++) acc[i] = 0;
-        for (uint32_t j0 = 0; j0 < k_rt; j0 += 4) {
-            uint4 d[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t j = j0 + u;
-                d[u] = make_uint4(0, 0, 0, 0);
-                if (j < k_rt) {
-                    d[u] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
-                    if (tail_bytes) d[u] = mask_tail(d[u], tail_bytes);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (j0 + u < k_rt) lookup16<false>(acc, d[u], tab_lane + (j0 + u) * tstride, xshift);
-        }
-    }
     uint32_t o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -259,67 +243,199 @@ __device__ __forceinline__ void column_rows(const uint8_t *sp, uint32_t stride, 
     for (int row = 0; row < 4; row++) r[row] = make_uint4(o[row][0], o[row][1], o[row][2], o[row][3]);
 }
 
+// One 16-byte column of one stripe.  Slot u of a lane in sub-warp q holds source u ^ q (see file
+// header); slots >= k (padding of a partial last group) hold zeros.
+//   sp     : address of this column in source 0 (uniform modes) / shard 0 (plan mode)
+//   kPlan  : source j lives at sp + src_off[j] (smem) instead of sp + j*stride
+template <int K, bool kPlan>
+__device__ __forceinline__ void column_load(const uint8_t *sp, uint32_t stride, const uint32_t *src_off,
+                                            uint32_t q, uint4 (&d)[slots_for_k(K)])
+{
+    constexpr int S = slots_for_k(K);
+#pragma unroll
+    for (int u = 0; u < S; u++) {
+        const uint32_t j = (uint32_t)u ^ q;
+        if (S == K || j < (uint32_t)K) d[u] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
+        else d[u] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// look up + transpose -> r[row] (uint4) for the slots of one column
+//   tab_base : shared address of the tables
+template <int K>
+__device__ __forceinline__ void column_compute(uint4 (&d)[slots_for_k(K)], uint32_t tab_base, uint32_t lane,
+                                               uint32_t row_bytes, uint32_t tail_bytes, uint4 (&r)[4])
+{
+    constexpr int S = slots_for_k(K);
+    constexpr int LG = log2_group_for_k(K);
+    constexpr uint32_t R = 32u >> LG;
+    uint32_t acc[16];
+    if (tail_bytes) {
+#pragma unroll
+        for (int u = 0; u < S; u++) d[u] = mask_tail(d[u], tail_bytes);
+    }
+#pragma unroll
+    for (int u = 0; u < S; u++) {
+        // group u >> LG, phase u & (G-1): this lane's bank is lane ^ (phase * R)
+        const uint32_t base = tab_base + ((lane ^ (((uint32_t)u & ((1u << LG) - 1)) * R)) << 2) +
+                              (uint32_t)(u >> LG) * kGroupBytes;
+        if (u == 0) lookup16<true>(acc, d[u], base, row_bytes);
+        else lookup16<false>(acc, d[u], base, row_bytes);
+    }
+    rows_from_acc(acc, r);
+}
+
+// generic k (runtime): one group of G slots at a time, no cross-column prefetch
+template <bool kPlan>
+__device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t stride, uint32_t k_rt,
+                                                    const uint32_t *src_off, uint32_t tab_base,
+                                                    uint32_t row_bytes, uint32_t tail_bytes, uint32_t lane,
+                                                    uint4 (&r)[4])
+{
+    const uint32_t lg = (uint32_t)log2_group_for_k((int)k_rt);
+    const uint32_t G = 1u << lg, R = 32u >> lg;
+    const uint32_t q = lane >> (5 - lg);
+    const uint32_t slots = (uint32_t)slots_for_k((int)k_rt);
+    uint32_t acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0;
+    for (uint32_t u0 = 0; u0 < slots; u0 += 4) {
+        uint4 d[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const uint32_t j = (u0 + v) ^ q;
+            d[v] = make_uint4(0, 0, 0, 0);
+            if (u0 + v < slots && j < k_rt) {
+                d[v] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
+                if (tail_bytes) d[v] = mask_tail(d[v], tail_bytes);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const uint32_t u = u0 + v;
+            if (u < slots) {
+                const uint32_t base = tab_base + ((lane ^ ((u & (G - 1)) * R)) << 2) + (u >> lg) * kGroupBytes;
+                lookup16<false>(acc, d[v], base, row_bytes);
+            }
+        }
+    }
+    rows_from_acc(acc, r);
+}
+
 // ------------------------------------------------------------------ the streaming kernel
 template <int K, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_constant__ ApplyParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemLayout L = carve(smem_raw, p.k, p.log2R);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const SmemLayout L = carve(smem_raw, p.k);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t k = (K > 0) ? (uint32_t)K : p.k;
+    constexpr int KD = K > 0 ? K : 1;
+    constexpr int SD = slots_for_k(KD);
 
     for (uint32_t i = tid; i < 512; i += kThreads) L.gf_exp[i] = c_gf_exp[i];
     for (uint32_t i = tid; i < 256; i += kThreads) L.gf_log[i] = c_gf_log[i];
     __syncthreads();
 
-    const uint32_t R = 1u << p.log2R;
-    const uint32_t tab_lane =
-        (uint32_t)__cvta_generic_to_shared(L.tab) + ((lane & (R - 1)) << 2);
+    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(L.tab);
+    const uint32_t q = lane >> (5 - log2_group_for_k((int)k));  // sub-warp index
 
     if (MODE != kModePlan) {
         // ---- uniform coefficient matrix: build once, then warps stream items ----------------
-        build_tables(L, p.coef, k, k, p.rows, p.log2R);
+        build_tables(L, p.coef, k, k, p.rows);
         __syncthreads();
 
         const uint32_t ips = p.items_per_stripe;
         const uint32_t total = p.n * ips;  // host guarantees < 2^32
         const uint32_t gwarps = gridDim.x * (kThreads / 32);
-        for (uint32_t item = blockIdx.x * (kThreads / 32) + warp; item < total; item += gwarps) {
-            const uint32_t s = item / ips;
-            const uint32_t c = item - s * ips;
-            const uint32_t len = p.shard_len ? __ldg(p.shard_len + s) : p.stride;
+
+        // position of this lane's column for a work item (stripe, 32-column chunk)
+        struct Pos {
+            const uint8_t *sp;
+            uint32_t s, col, tail;
+            bool valid;
+        };
+        auto locate = [&](uint32_t item) -> Pos {
+            Pos z;
+            z.s = item / ips;
+            const uint32_t c = item - z.s * ips;
+            const uint32_t len = p.shard_len ? __ldg(p.shard_len + z.s) : p.stride;
             const uint32_t nvec = (len + 15) >> 4;
-            const uint32_t col = c * 32 + lane;
+            z.col = c * 32 + lane;
+            z.valid = z.col < nvec;
+            z.tail = (z.col == nvec - 1) ? (len & 15) : 0;
+            z.sp = p.src + (unsigned long long)z.s * p.src_pitch + (size_t)z.col * 16;
+            return z;
+        };
+        auto finish = [&](const Pos &z, const uint4 (&r)[4]) {
             uint32_t mm = 0;
-            if (col < nvec) {
-                const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
-                const uint8_t *sp = p.src + (unsigned long long)s * p.src_pitch + (size_t)col * 16;
-                uint4 r[4];
-                column_rows<K, false>(sp, p.stride, k, nullptr, tab_lane, p.log2R, tail, r);
-                if (MODE == kModeEncode) {
-                    uint8_t *dp = p.dst + (unsigned long long)s * p.dst_pitch + (size_t)col * 16;
+            if (MODE == kModeEncode) {
+                if (z.valid) {
+                    uint8_t *dp = p.dst + (unsigned long long)z.s * p.dst_pitch + (size_t)z.col * 16;
 #pragma unroll
                     for (int i = 0; i < 4; i++)
                         if (i < (int)p.rows) stg_stream(dp + (size_t)i * p.stride, r[i]);
-                } else {
+                }
+            } else {
+                if (z.valid) {
                     // stored parity rows follow the k data shards of the same stripe
-                    const uint8_t *pp = sp + (size_t)(k + p.row_off) * p.stride;
+                    const uint8_t *pp = z.sp + (size_t)(k + p.row_off) * p.stride;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         if (i < (int)p.rows) {
                             uint4 st = ldg_stream(pp + (size_t)i * p.stride);
-                            if (tail) st = mask_tail(st, tail);
-                            const uint32_t diff = (st.x ^ r[i].x) | (st.y ^ r[i].y) |
-                                                  (st.z ^ r[i].z) | (st.w ^ r[i].w);
+                            if (z.tail) st = mask_tail(st, z.tail);
+                            const uint32_t diff = (st.x ^ r[i].x) | (st.y ^ r[i].y) | (st.z ^ r[i].z) |
+                                                  (st.w ^ r[i].w);
                             if (diff) mm |= 1u << (p.row_off + i);
                         }
                     }
                 }
-            }
-            if (MODE == kModeVerify) {
                 // warp-shuffle OR reduction of the per-lane mismatch bits, one atomic per warp
                 mm = __reduce_or_sync(0xffffffffu, mm);
-                if (mm && lane == 0) atomicOr(p.mismatch + s, mm);
+                if (mm && lane == 0) atomicOr(p.mismatch + z.s, mm);
+            }
+        };
+
+        uint32_t item = blockIdx.x * (kThreads / 32) + warp;
+        if (K > 0 && GEC_PIPELINE) {
+            uint4 dn[SD];
+            Pos nx;
+            nx.valid = false;
+            if (item < total) {
+                nx = locate(item);
+                if (nx.valid) column_load<KD, false>(nx.sp, p.stride, nullptr, q, dn);
+            }
+            while (item < total) {
+                uint4 d[SD];
+#pragma unroll
+                for (int u = 0; u < SD; u++) d[u] = dn[u];
+                const Pos cur = nx;
+                item += gwarps;
+                nx.valid = false;
+                if (item < total) {
+                    nx = locate(item);
+                    if (nx.valid) column_load<KD, false>(nx.sp, p.stride, nullptr, q, dn);
+                }
+                uint4 r[4];
+                if (cur.valid) column_compute<KD>(d, tab_base, lane, p.row_bytes, cur.tail, r);
+                finish(cur, r);
+            }
+        } else {
+            for (; item < total; item += gwarps) {
+                const Pos cur = locate(item);
+                uint4 r[4];
+                if (cur.valid) {
+                    if (K > 0) {
+                        uint4 d[SD];
+                        column_load<KD, false>(cur.sp, p.stride, nullptr, q, d);
+                        column_compute<KD>(d, tab_base, lane, p.row_bytes, cur.tail, r);
+                    } else {
+                        column_rows_generic<false>(cur.sp, p.stride, k, nullptr, tab_base, p.row_bytes,
+                                                   cur.tail, lane, r);
+                    }
+                }
+                finish(cur, r);
             }
         }
     } else {
@@ -343,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_cons
                 for (uint32_t e = tid; e < (uint32_t)rows * kMaxK; e += kThreads)
                     L.coef[e] = pl->coef[p.row_off + e / kMaxK][e % kMaxK];
                 __syncthreads();
-                build_tables(L, L.coef, kMaxK, k, (uint32_t)rows, p.log2R);
+                build_tables(L, L.coef, kMaxK, k, (uint32_t)rows);
                 __syncthreads();
                 prev_present = kp;
                 prev_out = ko;
@@ -353,14 +469,40 @@ __global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_cons
             const uint32_t nvec = (len + 15) >> 4;
             const uint8_t *sbase = p.src + (unsigned long long)s * p.src_pitch;
             uint8_t *dbase = p.dst + (unsigned long long)s * p.dst_pitch;
-            for (uint32_t col = tid; col < nvec; col += kThreads) {
-                const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
-                uint4 r[4];
-                column_rows<K, true>(sbase + (size_t)col * 16, p.stride, k, L.src_off, tab_lane,
-                                     p.log2R, tail, r);
+            if (K > 0 && GEC_PIPELINE) {
+                uint4 dn[SD];
+                uint32_t col = tid;
+                if (col < nvec) column_load<KD, true>(sbase + (size_t)col * 16, p.stride, L.src_off, q, dn);
+                while (col < nvec) {
+                    uint4 d[SD];
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (i < rows) stg_stream(dbase + L.dst_off[i] + (size_t)col * 16, r[i]);
+                    for (int u = 0; u < SD; u++) d[u] = dn[u];
+                    const uint32_t cur = col;
+                    col += kThreads;
+                    if (col < nvec) column_load<KD, true>(sbase + (size_t)col * 16, p.stride, L.src_off, q, dn);
+                    const uint32_t tail = (cur == nvec - 1) ? (len & 15) : 0;
+                    uint4 r[4];
+                    column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < rows) stg_stream(dbase + L.dst_off[i] + (size_t)cur * 16, r[i]);
+                }
+            } else {
+                for (uint32_t col = tid; col < nvec; col += kThreads) {
+                    const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
+                    uint4 r[4];
+                    if (K > 0) {
+                        uint4 d[SD];
+                        column_load<KD, true>(sbase + (size_t)col * 16, p.stride, L.src_off, q, d);
+                        column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
+                    } else {
+                        column_rows_generic<true>(sbase + (size_t)col * 16, p.stride, k, L.src_off, tab_base,
+                                                  p.row_bytes, tail, lane, r);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < rows) stg_stream(dbase + L.dst_off[i] + (size_t)col * 16, r[i]);
+                }
             }
         }
     }
