@@ -113,11 +113,17 @@ struct TimedLaunch {
 };
 
 // ---- kernel dispatch --------------------------------------------------------------------
+template <int MODE> struct LaunchShape;
+template <> struct LaunchShape<kModeEncode> { static constexpr int NT = GEC_NT_ENC; static constexpr bool PIPE = GEC_PIPE_ENC; };
+template <> struct LaunchShape<kModePlan> { static constexpr int NT = GEC_NT_PLAN; static constexpr bool PIPE = GEC_PIPE_PLAN; };
+template <> struct LaunchShape<kModeVerify> { static constexpr int NT = GEC_NT_VER; static constexpr bool PIPE = GEC_PIPE_VER; };
+
 template <int K, int MODE>
 cudaError_t launch_apply_t(const garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t st)
 {
     static std::atomic<int> configured_for_device{-1};  // per instantiation
-    auto kern = rs_apply_kernel<K, MODE>;
+    constexpr int NT = LaunchShape<MODE>::NT;
+    auto kern = rs_apply_kernel<K, MODE, NT, LaunchShape<MODE>::PIPE>;
     // opt-in shared memory size is a per-function, per-device attribute; setting it is cheap
     // but not free, so remember the last device it was set for.
     if (configured_for_device.load(std::memory_order_acquire) != ctx->device) {
@@ -126,7 +132,7 @@ cudaError_t launch_apply_t(const garage_ec_ctx *ctx, const ApplyParams &p, cudaS
         if (e != cudaSuccess) return e;
         configured_for_device.store(ctx->device, std::memory_order_release);
     }
-    kern<<<ctx->sm_count, kThreads, ctx->smem_bytes, st>>>(p);
+    kern<<<ctx->sm_count, NT, ctx->smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -135,8 +141,15 @@ cudaError_t launch_apply(garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t 
 {
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     switch (p.k) {
+#ifndef GEC_FAST_BUILD
+    case 2: return launch_apply_t<2, MODE>(ctx, p, st);
+    case 3: return launch_apply_t<3, MODE>(ctx, p, st);
     case 4: return launch_apply_t<4, MODE>(ctx, p, st);
+    case 5: return launch_apply_t<5, MODE>(ctx, p, st);
     case 6: return launch_apply_t<6, MODE>(ctx, p, st);
+    case 8: return launch_apply_t<8, MODE>(ctx, p, st);
+    case 12: return launch_apply_t<12, MODE>(ctx, p, st);
+#endif
     case 10: return launch_apply_t<10, MODE>(ctx, p, st);
     default: return launch_apply_t<0, MODE>(ctx, p, st);
     }

@@ -40,13 +40,28 @@
 
 namespace garage_ec {
 
-#ifndef GEC_THREADS
-#define GEC_THREADS 512
+// Launch shapes per mode (1 CTA per SM; tables fill shared memory).  PIPE = prefetch the next
+// column's k vectors into registers while the current one is processed.  Tuned on B200
+// (profiles/r01_variants.md): encode/reconstruct like fewer, fatter threads with the prefetch;
+// verify (k+m loads per column, no stores) likes more threads.
+#ifndef GEC_NT_ENC
+#define GEC_NT_ENC 512
 #endif
-#ifndef GEC_PIPELINE
-#define GEC_PIPELINE 1  // prefetch the next column's k vectors into registers while computing
+#ifndef GEC_PIPE_ENC
+#define GEC_PIPE_ENC 1
 #endif
-constexpr int kThreads = GEC_THREADS;  // threads per CTA; 1 CTA per SM (tables fill smem)
+#ifndef GEC_NT_PLAN
+#define GEC_NT_PLAN 512
+#endif
+#ifndef GEC_PIPE_PLAN
+#define GEC_PIPE_PLAN 1
+#endif
+#ifndef GEC_NT_VER
+#define GEC_NT_VER 1024
+#endif
+#ifndef GEC_PIPE_VER
+#define GEC_PIPE_VER 0
+#endif
 constexpr int kMaxK = 32;
 constexpr int kMaxM = 8;
 constexpr int kRowsPerPass = 4;  // output rows packed in one 32-bit table word
@@ -149,18 +164,21 @@ __device__ __forceinline__ void transpose4x4(const uint32_t a0, const uint32_t a
 }
 
 // ------------------------------------------------------------------ shared memory carve-up
-struct SmemLayout {
-    // dynamic smem: [table groups: ceil(k/G) * 32 KB][exp 512][log 256][src_off 32 u32]
-    //               [dst_off 4 u32][coef 4*32][sched 1 u32]
-    uint32_t *tab;
-    uint8_t *gf_exp;
-    uint8_t *gf_log;
-    uint32_t *src_off;
-    uint32_t *dst_off;
-    uint8_t *coef;
-    uint32_t *sched;
+// Decode plan of one stripe as the streaming kernel needs it (two slots: current / next).
+struct PlanSlot {
+    unsigned long long key_present, key_out;
+    uint32_t sid;   // stripe index (>= n: no more work)
+    int32_t rows;   // rows to produce in this pass (<= 0: nothing to do)
+    uint32_t src_off[kMaxK];           // byte offset of source j inside the stripe
+    uint32_t dst_off[kRowsPerPass];    // byte offset of output row i inside the stripe
+    uint8_t coef[kRowsPerPass * kMaxK];  // coef[i*kMaxK + j]
 };
-constexpr size_t kSmemAux = 512 + 256 + kMaxK * 4 + kRowsPerPass * 4 + kRowsPerPass * kMaxK + 16;
+struct SmemLayout {
+    // dynamic smem: [table groups: ceil(k/G) * 32 KB][PlanSlot x 2]
+    uint32_t *tab;
+    PlanSlot *slot;
+};
+constexpr size_t kSmemAux = 2 * sizeof(PlanSlot) + 16;
 __host__ __device__ inline size_t smem_bytes_for(int k)
 {
     return (size_t)(slots_for_k(k) >> log2_group_for_k(k)) * kGroupBytes + kSmemAux;
@@ -170,41 +188,88 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, uint32_t k)
 {
     SmemLayout L;
     L.tab = reinterpret_cast<uint32_t *>(base);
-    unsigned char *p = base + (size_t)(slots_for_k((int)k) >> log2_group_for_k((int)k)) * kGroupBytes;
-    L.gf_exp = p;
-    p += 512;
-    L.gf_log = p;
-    p += 256;
-    L.src_off = reinterpret_cast<uint32_t *>(p);
-    p += kMaxK * 4;
-    L.dst_off = reinterpret_cast<uint32_t *>(p);
-    p += kRowsPerPass * 4;
-    L.coef = p;
-    p += kRowsPerPass * kMaxK;
-    L.sched = reinterpret_cast<uint32_t *>(p);
+    L.slot = reinterpret_cast<PlanSlot *>(
+        base + (size_t)(slots_for_k((int)k) >> log2_group_for_k((int)k)) * kGroupBytes);
     return L;
 }
 
+// multiply four packed GF(2^8) bytes by alpha (= 2): shift left, reduce by 0x11D where bit 7 was set
+__device__ __forceinline__ uint32_t xtime4(uint32_t v)
+{
+    const uint32_t hi = v & 0x80808080u;
+    return ((v ^ hi) << 1) ^ ((hi >> 7) * 0x1du);
+}
+
 // Build the product tables for `rows` (<=4) coefficient rows coef[i*cstride + j], j < k; the
-// padding tables of a partial last group are all zero.  Caller syncs before and after.
+// padding tables of a partial last group are all zero.  No log/antilog lookups: entry x of
+// table j is XOR_{bit b of x} (packed column j) * alpha^b, split as Hi[x >> 4] ^ Lo[x & 15].
+// Caller syncs before and after.
+//  * G <= 2 (k <= 14): warp-cooperative.  Each lane keeps Lo[lane & 15] / Hi[lane & 15] of its
+//    sub-warp's table in two registers; an entry is two shuffles + XOR; one STS.128 instruction
+//    of a warp writes 4 rows x (all replicas) = 512 B over all 32 banks in the minimum 4
+//    wavefronts (a row-per-lane mapping would serialise 32-way on the replica banks).
+//  * G >= 4: plain loop (generic path).
+template <int NT>
 __device__ __forceinline__ void build_tables(const SmemLayout &L, const uint8_t *coef, uint32_t cstride,
                                              uint32_t k, uint32_t rows)
 {
     const uint32_t lg = (uint32_t)log2_group_for_k((int)k);
     const uint32_t slots = (uint32_t)slots_for_k((int)k);
     const uint32_t R = 32u >> lg;  // replicas per table = lanes per sub-warp (>= 4)
-    for (uint32_t e = threadIdx.x; e < slots * 256; e += kThreads) {
+    auto packed_col = [&](uint32_t j) -> uint32_t {
+        uint32_t cur = 0;
+        if (j < k) {
+#pragma unroll
+            for (uint32_t i = 0; i < kRowsPerPass; i++)
+                if (i < rows) cur |= (uint32_t)coef[i * cstride + j] << (8 * i);
+        }
+        return cur;
+    };
+    if (lg <= 1) {
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t sub = lg ? (lane >> 4) : 0;           // table of the group this lane writes
+        const uint32_t quads = R >> 2;                        // 16-byte pieces per row and table
+        const uint32_t quad = lane & (quads - 1);
+        const uint32_t xsel = (lane >> (lg ? 2 : 3)) & 3;     // which of the 4 rows of this instruction
+        const uint32_t total = (slots >> lg) * 64;            // STS.128 warp-instructions
+        const uint32_t per = (total + NT / 32 - 1) / (NT / 32);
+        const uint32_t i0 = warp * per, i1 = min(total, i0 + per);
+        uint32_t tprev = 0xffffffffu, lo = 0, hi = 0;
+        for (uint32_t I = i0; I < i1; I++) {
+            const uint32_t t = I >> 6, r4 = I & 63;
+            if (t != tprev) {
+                uint32_t cur = packed_col((t << lg) + sub);
+                const uint32_t idx = lane & 15;
+                lo = 0;
+                hi = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if ((idx >> b) & 1) lo ^= cur;
+                    cur = xtime4(cur);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if ((idx >> b) & 1) hi ^= cur;
+                    cur = xtime4(cur);
+                }
+                tprev = t;
+            }
+            const uint32_t x = r4 * 4 + xsel;
+            const uint32_t w = __shfl_sync(0xffffffffu, lo, (lane & 16) + (x & 15)) ^
+                               __shfl_sync(0xffffffffu, hi, (lane & 16) + (x >> 4));
+            uint32_t *dst = L.tab + (size_t)t * (kGroupBytes / 4) + x * 32 + sub * R + quad * 4;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(w, w, w, w);
+        }
+        return;
+    }
+    for (uint32_t e = threadIdx.x; e < slots * 256; e += NT) {
         const uint32_t j = e >> 8, x = e & 255;
         uint32_t w = 0;
-        if (x && j < k) {
-            const uint32_t lx = L.gf_log[x];
+        uint32_t cur = packed_col(j);
 #pragma unroll
-            for (uint32_t i = 0; i < kRowsPerPass; i++) {
-                if (i < rows) {
-                    const uint32_t c = coef[i * cstride + j];
-                    if (c) w |= (uint32_t)L.gf_exp[L.gf_log[c] + lx] << (8 * i);
-                }
-            }
+        for (int b = 0; b < 8; b++) {
+            if ((x >> b) & 1) w ^= cur;
+            cur = xtime4(cur);
         }
         // table j: group t = j >> lg, banks [sub*R, sub*R + R), row x
         uint32_t *dst = L.tab + (size_t)(j >> lg) * (kGroupBytes / 4) + x * 32 + (j & ((1u << lg) - 1)) * R;
@@ -323,9 +388,10 @@ __device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t 
 }
 
 // ------------------------------------------------------------------ the streaming kernel
-template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_constant__ ApplyParams p)
+template <int K, int MODE, int NT, bool PIPE>
+__global__ void __launch_bounds__(NT, 1) rs_apply_kernel(const __grid_constant__ ApplyParams p)
 {
+    constexpr int kThreads = NT;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const SmemLayout L = carve(smem_raw, p.k);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -333,16 +399,12 @@ __global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_cons
     constexpr int KD = K > 0 ? K : 1;
     constexpr int SD = slots_for_k(KD);
 
-    for (uint32_t i = tid; i < 512; i += kThreads) L.gf_exp[i] = c_gf_exp[i];
-    for (uint32_t i = tid; i < 256; i += kThreads) L.gf_log[i] = c_gf_log[i];
-    __syncthreads();
-
     const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(L.tab);
     const uint32_t q = lane >> (5 - log2_group_for_k((int)k));  // sub-warp index
 
     if (MODE != kModePlan) {
         // ---- uniform coefficient matrix: build once, then warps stream items ----------------
-        build_tables(L, p.coef, k, k, p.rows);
+        build_tables<NT>(L, p.coef, k, k, p.rows);
         __syncthreads();
 
         const uint32_t ips = p.items_per_stripe;
@@ -398,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_cons
         };
 
         uint32_t item = blockIdx.x * (kThreads / 32) + warp;
-        if (K > 0 && GEC_PIPELINE) {
+        if (K > 0 && PIPE) {
             uint4 dn[SD];
             Pos nx;
             nx.valid = false;
@@ -440,70 +502,113 @@ __global__ void __launch_bounds__(kThreads, 1) rs_apply_kernel(const __grid_cons
         }
     } else {
         // ---- per-stripe matrices: CTAs pull stripes from an atomic counter -------------------
-        unsigned long long prev_present = ~0ull, prev_out = ~0ull;
-        bool have_tables = false;
-        for (;;) {
-            __syncthreads();  // previous stripe's tables / offsets no longer in use
-            if (tid == 0) *L.sched = atomicAdd(p.counter, 1u);
-            __syncthreads();
-            const uint32_t s = *L.sched;
-            if (s >= p.n) break;
-            const StripePlan *pl = p.plan + s;
-            const int nrows_total = pl->nrows;
-            const int rows = min(kRowsPerPass, nrows_total - (int)p.row_off);
-            if (pl->unrecoverable || rows <= 0) continue;
-            const unsigned long long kp = pl->key_present, ko = pl->key_out;
-            if (!(have_tables && kp == prev_present && ko == prev_out)) {
-                if (tid < k) L.src_off[tid] = (uint32_t)pl->surv[tid] * p.stride;
-                if (tid < (uint32_t)rows) L.dst_off[tid] = (uint32_t)pl->out_idx[p.row_off + tid] * p.stride;
-                for (uint32_t e = tid; e < (uint32_t)rows * kMaxK; e += kThreads)
-                    L.coef[e] = pl->coef[p.row_off + e / kMaxK][e % kMaxK];
-                __syncthreads();
-                build_tables(L, L.coef, kMaxK, k, (uint32_t)rows);
-                __syncthreads();
-                prev_present = kp;
-                prev_out = ko;
-                have_tables = true;
+        // Two plan slots: while the CTA streams stripe `cur`, warp 0 claims the next stripe and
+        // stages its plan; at the stripe boundary the first column loads of the new stripe are
+        // issued BEFORE its tables are rebuilt, so HBM latency hides behind the rebuild.
+        auto stage_plan = [&](PlanSlot &ps) {  // executed by warp 0 only
+            uint32_t s = 0;
+            if (lane == 0) s = atomicAdd(p.counter, 1u);
+            s = __shfl_sync(0xffffffffu, s, 0);
+            int rows = 0;
+            if (s < p.n) {
+                const StripePlan *pl = p.plan + s;
+                rows = pl->unrecoverable ? 0 : min(kRowsPerPass, (int)pl->nrows - (int)p.row_off);
+                if (rows > 0) {
+                    if (lane < k) ps.src_off[lane] = (uint32_t)pl->surv[lane] * p.stride;
+                    if (lane < (uint32_t)rows) ps.dst_off[lane] = (uint32_t)pl->out_idx[p.row_off + lane] * p.stride;
+                    for (uint32_t e = lane; e < (uint32_t)rows * kMaxK; e += 32)
+                        ps.coef[e] = pl->coef[p.row_off + e / kMaxK][e % kMaxK];
+                    if (lane == 0) {
+                        ps.key_present = pl->key_present;
+                        ps.key_out = pl->key_out;
+                    }
+                }
             }
-            const uint32_t len = p.shard_len ? __ldg(p.shard_len + s) : p.stride;
-            const uint32_t nvec = (len + 15) >> 4;
+            if (lane == 0) {
+                ps.sid = s;
+                ps.rows = rows;
+            }
+        };
+        if (warp == 0) stage_plan(L.slot[0]);
+        __syncthreads();
+        unsigned long long built_present = ~0ull, built_out = ~0ull;
+        bool have_tables = false;
+        bool have_dn = false;  // dn already holds this thread's first column of the stripe in slot cs
+        uint4 dn[SD];
+        for (uint32_t cs = 0;; cs ^= 1) {
+            const PlanSlot &ps = L.slot[cs];
+            const uint32_t s = ps.sid;
+            if (s >= p.n) break;
+            const int rows = ps.rows;
+            uint32_t len = 0, nvec = 0;
             const uint8_t *sbase = p.src + (unsigned long long)s * p.src_pitch;
             uint8_t *dbase = p.dst + (unsigned long long)s * p.dst_pitch;
-            if (K > 0 && GEC_PIPELINE) {
-                uint4 dn[SD];
-                uint32_t col = tid;
-                if (col < nvec) column_load<KD, true>(sbase + (size_t)col * 16, p.stride, L.src_off, q, dn);
-                while (col < nvec) {
-                    uint4 d[SD];
-#pragma unroll
-                    for (int u = 0; u < SD; u++) d[u] = dn[u];
-                    const uint32_t cur = col;
-                    col += kThreads;
-                    if (col < nvec) column_load<KD, true>(sbase + (size_t)col * 16, p.stride, L.src_off, q, dn);
-                    const uint32_t tail = (cur == nvec - 1) ? (len & 15) : 0;
-                    uint4 r[4];
-                    column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (i < rows) stg_stream(dbase + L.dst_off[i] + (size_t)cur * 16, r[i]);
-                }
-            } else {
-                for (uint32_t col = tid; col < nvec; col += kThreads) {
-                    const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
-                    uint4 r[4];
-                    if (K > 0) {
+            uint32_t col = tid;
+            if (rows > 0) {
+                len = p.shard_len ? __ldg(p.shard_len + s) : p.stride;
+                nvec = (len + 15) >> 4;
+                if (K > 0 && PIPE && col < nvec && !have_dn)
+                    column_load<KD, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, q, dn);
+            }
+            have_dn = false;
+            if (warp == 0) stage_plan(L.slot[cs ^ 1]);
+            if (rows > 0 && !(have_tables && ps.key_present == built_present && ps.key_out == built_out)) {
+                build_tables<NT>(L, ps.coef, kMaxK, k, (uint32_t)rows);
+                built_present = ps.key_present;
+                built_out = ps.key_out;
+                have_tables = true;
+            }
+            __syncthreads();  // tables of `s` complete, next plan staged
+            if (rows > 0) {
+                if (K > 0 && PIPE) {
+                    while (col < nvec) {
                         uint4 d[SD];
-                        column_load<KD, true>(sbase + (size_t)col * 16, p.stride, L.src_off, q, d);
-                        column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
-                    } else {
-                        column_rows_generic<true>(sbase + (size_t)col * 16, p.stride, k, L.src_off, tab_base,
-                                                  p.row_bytes, tail, lane, r);
-                    }
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (i < rows) stg_stream(dbase + L.dst_off[i] + (size_t)col * 16, r[i]);
+                        for (int u = 0; u < SD; u++) d[u] = dn[u];
+                        const uint32_t cur = col;
+                        col += kThreads;
+                        if (col < nvec) {
+                            column_load<KD, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, q, dn);
+                        } else {
+                            // last column of this thread in this stripe: start on the next stripe
+                            // (its plan was staged before the barrier above) so HBM never drains
+                            const PlanSlot &nx = L.slot[cs ^ 1];
+                            if (nx.sid < p.n && nx.rows > 0) {
+                                const uint32_t nlen = p.shard_len ? __ldg(p.shard_len + nx.sid) : p.stride;
+                                if (tid < ((nlen + 15) >> 4)) {
+                                    column_load<KD, true>(p.src + (unsigned long long)nx.sid * p.src_pitch +
+                                                              (size_t)tid * 16,
+                                                          p.stride, nx.src_off, q, dn);
+                                    have_dn = true;
+                                }
+                            }
+                        }
+                        const uint32_t tail = (cur == nvec - 1) ? (len & 15) : 0;
+                        uint4 r[4];
+                        column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (i < rows) stg_stream(dbase + ps.dst_off[i] + (size_t)cur * 16, r[i]);
+                    }
+                } else {
+                    for (; col < nvec; col += kThreads) {
+                        const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
+                        uint4 r[4];
+                        if (K > 0) {
+                            uint4 d[SD];
+                            column_load<KD, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, q, d);
+                            column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
+                        } else {
+                            column_rows_generic<true>(sbase + (size_t)col * 16, p.stride, k, ps.src_off, tab_base,
+                                                      p.row_bytes, tail, lane, r);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (i < rows) stg_stream(dbase + ps.dst_off[i] + (size_t)col * 16, r[i]);
+                    }
                 }
             }
+            __syncthreads();  // tables and slot `cs` are free again
         }
     }
 }
