@@ -219,19 +219,18 @@ def run_ours(args, rank, world, local_rank):
     k, m, n = args.k, args.m, args.blocks
     tot = k + m
 
-    # rank 0 owns the generator matrix and the block ranges; NCCL broadcast
+    # rank 0 owns the generator matrix and the block ranges; one NCCL broadcast
     if world > 1:
-        ctrl = torch.zeros(m * k, dtype=torch.uint8, device=dev)
-        ranges = torch.zeros(world, 2, dtype=torch.int64, device=dev)
+        from garage_b200 import dist as D
+
+        P0 = ranges0 = None
         if rank == 0:
             with G.GarageEc(local_rank, k, m, G.VANDERMONDE) as tmp:
-                ctrl.copy_(torch.from_numpy(tmp.matrix().reshape(-1)))
-            for r in range(world):
-                ranges[r, 0], ranges[r, 1] = r * n, (r + 1) * n
-        dist.broadcast(ctrl, 0)
-        dist.broadcast(ranges, 0)
-        P = ctrl.cpu().numpy().reshape(m, k)
-        first_block = int(ranges[rank, 0])
+                P0 = tmp.matrix()
+            ranges0 = D.partition_blocks(n * world, world)
+        P, ranges = D.broadcast_control(k, m, P0, ranges0, dev, dist)
+        first_block = ranges[rank][0]
+        assert ranges[rank][1] - first_block == n
         enc = G.GarageEc(local_rank, k, m, matrix=P)
         dec = G.GarageEc(local_rank, k, m, matrix=P)
     else:
