@@ -108,7 +108,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.err = repr(e)
                 break
-            self._stop.wait(0.002)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         if self.nv:
@@ -420,7 +420,7 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
     assert ok, "e2e results differ from the device-resident pass"
     res = {
         "value": 2 * n * B * world * steps / el / GIB, "unit": "GiB/s", "steps": steps, "blocks_per_step": n,
-        "h2d_bytes_per_step": int(n * k * stride + n * tot * stride + 2 * n * 4 + n * tot),
+        "h2d_bytes_per_step": int(n * k * stride + n * k * stride + 2 * n * 4 + n * tot),  # encode data + the k survivors
         "d2h_bytes_per_step": int(n * m * stride + n * m * ((L + 15) // 16 * 16) + n * 4),
         "api": "garage_ec_encode + garage_ec_reconstruct, GARAGE_EC_MEM_HOST, pinned buffers from garage_ec_host_alloc",
         "timer": "host wall clock around synchronous calls (max over ranks)", "checked": bool(ok),

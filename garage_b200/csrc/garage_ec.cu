@@ -51,6 +51,7 @@ struct garage_ec_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
     std::vector<cudaEvent_t> free_events;
     std::atomic<uint64_t> launches{0};
+    std::atomic<int> batch_copy_ok{1};  // cudaMemcpyBatchAsync usable (cleared on first failure)
     char last_error[256] = {0};
 };
 
@@ -243,6 +244,53 @@ int run_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
 }
 
 size_t plan_scratch_bytes(size_t n) { return n * sizeof(StripePlan) + 16; }
+
+// ---- batched async copies ---------------------------------------------------------------
+// Reconstruct moves many shard-sized pieces per stripe (only the k survivors go up, only the
+// rebuilt shards come back).  One cudaMemcpyBatchAsync per chunk instead of thousands of
+// cudaMemcpyAsync calls keeps the CPU off the critical path; adjacent pieces are merged.
+struct CopyBatch {
+    std::vector<void *> dst, src;
+    std::vector<size_t> sz;
+    void add(void *d, const void *s, size_t n)
+    {
+        if (!n) return;
+        if (!dst.empty() && static_cast<uint8_t *>(dst.back()) + sz.back() == d &&
+            static_cast<const uint8_t *>(src.back()) + sz.back() == s) {
+            sz.back() += n;
+            return;
+        }
+        dst.push_back(d);
+        src.push_back(const_cast<void *>(s));
+        sz.push_back(n);
+    }
+    int flush(garage_ec_ctx *ctx, cudaMemcpyKind kind, cudaStream_t st)
+    {
+        const size_t cnt = dst.size();
+        if (!cnt) return GARAGE_EC_OK;
+        bool done = false;
+        if (cnt > 1 && ctx->batch_copy_ok.load(std::memory_order_relaxed)) {
+            cudaMemcpyAttributes attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+            size_t attr_idx = 0, fail = 0;
+            cudaError_t e = cudaMemcpyBatchAsync(dst.data(), src.data(), sz.data(), cnt, &attr, &attr_idx, 1,
+                                                 &fail, st);
+            if (e == cudaSuccess) {
+                done = true;
+            } else {
+                (void)cudaGetLastError();
+                ctx->batch_copy_ok.store(0, std::memory_order_relaxed);
+            }
+        }
+        if (!done)
+            for (size_t i = 0; i < cnt; i++) CU_TRY(ctx, cudaMemcpyAsync(dst[i], src[i], sz[i], kind, st));
+        dst.clear();
+        src.clear();
+        sz.clear();
+        return GARAGE_EC_OK;
+    }
+};
 
 // ---- host lanes -----------------------------------------------------------------------
 int lane_reserve(garage_ec_ctx *ctx, HostLane &L, size_t buf_bytes, size_t small_bytes)
@@ -598,13 +646,32 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
     }
     std::vector<int32_t> st_host(status ? 0 : n);
     int32_t *st_out = status ? status : st_host.data();
+    CopyBatch up, down;
+    int rc = GARAGE_EC_OK;
     size_t c = 0;
     for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
         HostLane &L = ctx->lanes[c % kHostLanes];
         const size_t cnt = n - s0 < cs ? n - s0 : cs;
         uint8_t *d_sh = L.d_buf;
-        CU_TRY(ctx, cudaMemcpyAsync(d_sh, shards + s0 * tot * stride, cnt * tot * stride,
-                                    cudaMemcpyHostToDevice, L.stream));
+        // H2D: only the k survivors (first k present shards) of stripes that have work to do
+        for (size_t s = s0; s < s0 + cnt; s++) {
+            const uint8_t *pr = present + s * tot;
+            size_t np = 0;
+            bool work = false;
+            for (size_t i = 0; i < tot; i++) {
+                np += pr[i] ? 1 : 0;
+                work |= !pr[i] && (!want || want[s * tot + i]);
+            }
+            if (np < k || !work) continue;
+            size_t used = 0;
+            for (size_t i = 0; i < tot && used < k; i++) {
+                if (!pr[i]) continue;
+                up.add(d_sh + ((s - s0) * tot + i) * stride, shards + (s * tot + i) * stride, stride);
+                used++;
+            }
+        }
+        rc = up.flush(ctx, cudaMemcpyHostToDevice, L.stream);
+        if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_present, present + s0 * tot, cnt * tot,
                                     cudaMemcpyHostToDevice, L.stream));
         const uint8_t *d_want = nullptr;
@@ -621,13 +688,13 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
         }
         StripePlan *d_plan = reinterpret_cast<StripePlan *>(L.d_small + o_plan);
         uint32_t *d_counter = reinterpret_cast<uint32_t *>(L.d_small + o_plan + cnt * sizeof(StripePlan));
-        int rc = run_reconstruct(ctx, d_sh, L.d_small + o_present, d_want,
-                                 reinterpret_cast<int32_t *>(L.d_small + o_status), d_len, stride, cnt,
-                                 d_plan, d_counter, L.stream);
+        rc = run_reconstruct(ctx, d_sh, L.d_small + o_present, d_want,
+                             reinterpret_cast<int32_t *>(L.d_small + o_status), d_len, stride, cnt,
+                             d_plan, d_counter, L.stream);
         if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(st_out + s0, L.d_small + o_status, cnt * 4, cudaMemcpyDeviceToHost,
                                     L.stream));
-        // copy back exactly the shards that were rebuilt
+        // D2H: exactly the shards that were rebuilt
         for (size_t s = s0; s < s0 + cnt; s++) {
             const uint8_t *pr = present + s * tot;
             size_t np = 0;
@@ -637,11 +704,11 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
             const size_t bytes = align_up(len, 16);
             for (size_t i = 0; i < tot; i++) {
                 if (pr[i] || (want && !want[s * tot + i])) continue;
-                CU_TRY(ctx, cudaMemcpyAsync(shards + (s * tot + i) * stride,
-                                            d_sh + ((s - s0) * tot + i) * stride, bytes,
-                                            cudaMemcpyDeviceToHost, L.stream));
+                down.add(shards + (s * tot + i) * stride, d_sh + ((s - s0) * tot + i) * stride, bytes);
             }
         }
+        rc = down.flush(ctx, cudaMemcpyDeviceToHost, L.stream);
+        if (rc) return rc;
     }
     for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     for (size_t s = 0; s < n; s++)
