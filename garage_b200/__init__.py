@@ -32,6 +32,8 @@ ABI_SYMBOLS = [
     "garage_ec_verify", "garage_ec_encode_blocks", "garage_ec_decode_blocks",
     "garage_ec_fill_random", "garage_ec_host_alloc", "garage_ec_host_free",
     "garage_ec_launch_count", "garage_ec_set_timing", "garage_ec_timing_read",
+    "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
+    "garage_ec_encode_blocks_with_sums",
 ]
 
 
@@ -83,6 +85,11 @@ def load_library(build=True):
     L.garage_ec_reconstruct.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz, i32, vp]
     L.garage_ec_verify.argtypes = [vp, vp, vp, vp, sz, sz, i32, vp]
     L.garage_ec_encode_blocks.argtypes = [vp, vp, vp, sz, vp, sz]
+    L.garage_ec_encode_blocks_with_sums.argtypes = [vp, vp, vp, sz, vp, vp, sz]
+    L.garage_ec_shard_sums.argtypes = [vp, vp, vp, sz, sz, i32, vp, i32, vp]
+    L.garage_ec_check_sums.argtypes = [vp, vp, vp, vp, sz, sz, i32, vp, i32, vp]
+    L.garage_ec_blake2sum.argtypes = [vp, sz, vp]
+    L.garage_ec_blake2sum.restype = None
     L.garage_ec_decode_blocks.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp]
     L.garage_ec_fill_random.argtypes = [vp, vp, sz, u64, u64, vp]
     L.garage_ec_host_alloc.argtypes = [vp, C.POINTER(vp), sz]
@@ -94,6 +101,15 @@ def load_library(build=True):
     L.garage_ec_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     _lib = L
     return L
+
+
+def blake2sum(data) -> bytes:
+    """Garage's blake2sum (BLAKE2b-512 truncated to 32 bytes) through the library's host code."""
+    L = load_library()
+    a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    out = np.zeros(32, dtype=np.uint8)
+    L.garage_ec_blake2sum(C.c_void_p(a.ctypes.data) if a.size else None, a.size, C.c_void_p(out.ctypes.data))
+    return out.tobytes()
 
 
 def _ptr(x):
@@ -210,14 +226,26 @@ class GarageEc:
         return self._check(self._L.garage_ec_verify(self._h, _ptr(shards), _ptr(mismatch), _ptr(shard_len),
                                                     stride, n, kind, st))
 
+    # -- per-shard integrity (blake2sum of every shard)
+    def shard_sums(self, shards, sums_out, stride, n, per_stripe, shard_len=None):
+        kind, st = self._stream(shards)
+        return self._check(self._L.garage_ec_shard_sums(self._h, _ptr(shards), _ptr(shard_len), stride, n,
+                                                        per_stripe, _ptr(sums_out), kind, st))
+
+    def check_sums(self, shards, expect, bad_out, stride, n, per_stripe, shard_len=None):
+        kind, st = self._stream(shards)
+        return self._check(self._L.garage_ec_check_sums(self._h, _ptr(shards), _ptr(expect), _ptr(shard_len),
+                                                        stride, n, per_stripe, _ptr(bad_out), kind, st))
+
     # -- block-level host API
-    def encode_blocks(self, blocks, parity_out, stride):
-        """blocks: list of 1-D uint8 numpy arrays; parity_out: numpy (n*m*stride)."""
+    def encode_blocks(self, blocks, parity_out, stride, sums_out=None):
+        """blocks: list of 1-D uint8 numpy arrays; parity_out: numpy (n*m*stride);
+        sums_out: optional numpy n*(k+m)*32 for the per-shard blake2sums."""
         n = len(blocks)
         ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in blocks])
         lens = np.array([b.size for b in blocks], dtype=np.uint32)
-        return self._check(self._L.garage_ec_encode_blocks(self._h, C.cast(ptrs, C.c_void_p), _ptr(lens), n,
-                                                           _ptr(parity_out), stride))
+        return self._check(self._L.garage_ec_encode_blocks_with_sums(self._h, C.cast(ptrs, C.c_void_p), _ptr(lens),
+                                                                     n, _ptr(parity_out), _ptr(sums_out), stride))
 
     def decode_blocks(self, shards, present, block_lens, stride, blocks_out, status=None):
         n = len(blocks_out)

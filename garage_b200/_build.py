@@ -53,7 +53,30 @@ def build(force=False, verbose=False):
     return SO
 
 
+BM_SO = os.path.join(PKG, "libgarage_block.so")
+BM_DEPS = [os.path.join(CSRC, "block_manager.cpp"), os.path.join(ROOT, "include", "garage_block_manager.h"),
+           os.path.join(ROOT, "include", "garage_ec.h")]
+
+
+def build_block_manager(force=False):
+    """C++ host mirror of BlockManager (libgarage_block.so): plain g++, links only the C ABI."""
+    build(force=False)
+    if (not force and os.path.exists(BM_SO)
+            and all(os.path.getmtime(d) <= os.path.getmtime(BM_SO) for d in BM_DEPS if os.path.exists(d))
+            and os.path.getmtime(SO) <= os.path.getmtime(BM_SO)):
+        return BM_SO
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wall", "-Wextra",
+           "-I", os.path.join(ROOT, "include"), BM_DEPS[0], "-L", PKG, "-lgarage_ec",
+           "-Wl,-rpath,$ORIGIN", "-o", BM_SO]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return BM_SO
+
+
 if __name__ == "__main__":
     import sys
 
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_block_manager(force="--force" in sys.argv))

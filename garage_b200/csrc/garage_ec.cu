@@ -114,17 +114,29 @@ struct TimedLaunch {
 };
 
 // ---- kernel dispatch --------------------------------------------------------------------
-template <int MODE> struct LaunchShape;
-template <> struct LaunchShape<kModeEncode> { static constexpr int NT = GEC_NT_ENC; static constexpr bool PIPE = GEC_PIPE_ENC; };
-template <> struct LaunchShape<kModePlan> { static constexpr int NT = GEC_NT_PLAN; static constexpr bool PIPE = GEC_PIPE_PLAN; };
-template <> struct LaunchShape<kModeVerify> { static constexpr int NT = GEC_NT_VER; static constexpr bool PIPE = GEC_PIPE_VER; };
+// Launch shape per (mode, K), tuned on B200 (profiles/r01_summary.md): few sources per column
+// leave registers for more warps (latency hiding); k >= 9 wants 512 fat threads with prefetch.
+template <int MODE, int K> struct LaunchShape {
+    static constexpr int NT = (GEC_NT_ENC != 512) ? GEC_NT_ENC
+                              : (K == 0 ? 512 : (K <= 4 ? 1024 : (K <= 6 ? 768 : (K <= 8 ? 640 : 512))));
+    static constexpr bool PIPE = GEC_PIPE_ENC;
+};
+template <int K> struct LaunchShape<kModePlan, K> {
+    static constexpr int NT = (GEC_NT_PLAN != 512) ? GEC_NT_PLAN
+                              : (K == 0 ? 512 : (K <= 4 ? 1024 : (K <= 6 ? 768 : (K <= 8 ? 640 : 512))));
+    static constexpr bool PIPE = GEC_PIPE_PLAN;
+};
+template <int K> struct LaunchShape<kModeVerify, K> {
+    static constexpr int NT = GEC_NT_VER;
+    static constexpr bool PIPE = GEC_PIPE_VER || (K > 0 && K <= 4);
+};
 
 template <int K, int MODE>
 cudaError_t launch_apply_t(const garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t st)
 {
     static std::atomic<int> configured_for_device{-1};  // per instantiation
-    constexpr int NT = LaunchShape<MODE>::NT;
-    auto kern = rs_apply_kernel<K, MODE, NT, LaunchShape<MODE>::PIPE>;
+    constexpr int NT = LaunchShape<MODE, K>::NT;
+    auto kern = rs_apply_kernel<K, MODE, NT, LaunchShape<MODE, K>::PIPE>;
     // opt-in shared memory size is a per-function, per-device attribute; setting it is cheap
     // but not free, so remember the last device it was set for.
     if (configured_for_device.load(std::memory_order_acquire) != ctx->device) {
@@ -743,6 +755,107 @@ int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *pr
     return GARAGE_EC_OK;
 }
 
+// --------------------------------------------------------------------------- SHARD SUMS
+static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *expect, const uint32_t *shard_len,
+                    size_t stride, size_t n_shards, int per_stripe, uint8_t *sums, uint8_t *bad, cudaStream_t st,
+                    int out_per_stripe = 0, int out_off = 0)
+{
+    SumParams q;
+    memset(&q, 0, sizeof(q));
+    q.base = shards;
+    q.shard_len = shard_len;
+    q.expect = expect;
+    q.sums = sums;
+    q.bad = bad;
+    q.stride = (uint32_t)stride;
+    q.per_stripe = (uint32_t)per_stripe;
+    q.n_shards = (uint32_t)n_shards;
+    q.out_per_stripe = (uint32_t)(out_per_stripe ? out_per_stripe : per_stripe);
+    q.out_off = (uint32_t)out_off;
+    blake2sum_shards_kernel<<<(unsigned)((n_shards + 127) / 128), 128, 0, st>>>(q);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "blake2sum_shards_kernel launch");
+    return GARAGE_EC_OK;
+}
+
+static int sums_common(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *expect, const uint32_t *shard_len,
+                       size_t stride, size_t n, int per, uint8_t *sums_out, uint8_t *bad_out, int mem_kind,
+                       void *cuda_stream)
+{
+    if (!ctx || (mem_kind != GARAGE_EC_MEM_HOST && mem_kind != GARAGE_EC_MEM_DEVICE)) return GARAGE_EC_E_INVALID;
+    if (per < 1 || per > kMaxK + kMaxM) return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n, per);
+    if (rc) return rc;
+    if (n == 0) return GARAGE_EC_OK;
+    if (!shards || (!sums_out && !bad_out)) return GARAGE_EC_E_INVALID;
+    if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
+    if (n * (size_t)per > 0xffffffffull) return GARAGE_EC_E_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mem_kind == GARAGE_EC_MEM_DEVICE)
+        return run_sums(ctx, shards, expect, shard_len, stride, n * per, per, sums_out, bad_out,
+                        (cudaStream_t)cuda_stream);
+    // HOST: chunked through the lanes (H2D shards [+ expect], kernel, D2H sums / bad flags)
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+    size_t cs = kHostChunkBytes / ((size_t)per * stride);
+    if (cs < 1) cs = 1;
+    if (cs > n) cs = n;
+    const size_t o_len = 0, o_exp = align_up(cs * 4, 16), o_sum = o_exp + cs * per * 32, o_bad = o_sum + cs * per * 32;
+    const size_t small = o_bad + align_up(cs * per, 16);
+    for (HostLane &L : ctx->lanes) {
+        rc = lane_reserve(ctx, L, cs * per * stride, small);
+        if (rc) return rc;
+    }
+    size_t c = 0;
+    for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
+        HostLane &L = ctx->lanes[c % kHostLanes];
+        const size_t cnt = n - s0 < cs ? n - s0 : cs;
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, shards + s0 * per * stride, cnt * per * stride, cudaMemcpyHostToDevice,
+                                    L.stream));
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_len, shard_len + s0, cnt * 4, cudaMemcpyHostToDevice, L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small + o_len);
+        }
+        const uint8_t *d_exp = nullptr;
+        if (expect) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_exp, expect + s0 * per * 32, cnt * per * 32,
+                                        cudaMemcpyHostToDevice, L.stream));
+            d_exp = L.d_small + o_exp;
+        }
+        rc = run_sums(ctx, L.d_buf, d_exp, d_len, stride, cnt * per, per, sums_out ? L.d_small + o_sum : nullptr,
+                      bad_out ? L.d_small + o_bad : nullptr, L.stream);
+        if (rc) return rc;
+        if (sums_out)
+            CU_TRY(ctx, cudaMemcpyAsync(sums_out + s0 * per * 32, L.d_small + o_sum, cnt * per * 32,
+                                        cudaMemcpyDeviceToHost, L.stream));
+        if (bad_out)
+            CU_TRY(ctx, cudaMemcpyAsync(bad_out + s0 * per, L.d_small + o_bad, cnt * per, cudaMemcpyDeviceToHost,
+                                        L.stream));
+    }
+    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_shard_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint32_t *shard_len, size_t stride,
+                         size_t n_stripes, int shards_per_stripe, uint8_t *sums_out, int mem_kind, void *cuda_stream)
+{
+    if (!sums_out) return GARAGE_EC_E_INVALID;
+    return sums_common(ctx, shards, nullptr, shard_len, stride, n_stripes, shards_per_stripe, sums_out, nullptr,
+                       mem_kind, cuda_stream);
+}
+
+int garage_ec_check_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *expect, const uint32_t *shard_len,
+                         size_t stride, size_t n_stripes, int shards_per_stripe, uint8_t *bad_out, int mem_kind,
+                         void *cuda_stream)
+{
+    if (!expect || !bad_out) return GARAGE_EC_E_INVALID;
+    return sums_common(ctx, shards, expect, shard_len, stride, n_stripes, shards_per_stripe, nullptr, bad_out,
+                       mem_kind, cuda_stream);
+}
+
+void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]) { blake2sum_host(data, len, out32); }
+
 // --------------------------------------------------------------------------- BLOCK-LEVEL
 // H2D of one block split into k zero-padded shards at dst (device, shard layout).
 static int upload_block_split(garage_ec_ctx *ctx, const uint8_t *block, uint32_t block_len, size_t k,
@@ -766,6 +879,12 @@ static int upload_block_split(garage_ec_ctx *ctx, const uint8_t *block, uint32_t
 int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks, const uint32_t *block_len,
                             size_t n_blocks, uint8_t *parity_out, size_t stride)
 {
+    return garage_ec_encode_blocks_with_sums(ctx, blocks, block_len, n_blocks, parity_out, nullptr, stride);
+}
+
+int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *blocks, const uint32_t *block_len,
+                                      size_t n_blocks, uint8_t *parity_out, uint8_t *sums_out, size_t stride)
+{
     if (!ctx) return GARAGE_EC_E_INVALID;
     int rc = check_geometry(ctx, stride, n_blocks, ctx->k + ctx->m);
     if (rc) return rc;
@@ -783,9 +902,10 @@ int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks, co
     if (cs > n_blocks) cs = n_blocks;
     const size_t in_b = cs * k * stride, out_b = cs * m * stride;
     for (HostLane &L : ctx->lanes) {
-        rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16));
+        rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16) + cs * (k + m) * 32);
         if (rc) return rc;
     }
+    const size_t o_sums = align_up(cs * 4, 16);
     std::vector<uint32_t> lens(cs * kHostLanes);
     size_t c = 0;
     for (size_t s0 = 0; s0 < n_blocks; s0 += cs, c++) {
@@ -807,6 +927,18 @@ int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks, co
         if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(parity_out + s0 * m * stride, L.d_buf + in_b, cnt * m * stride,
                                     cudaMemcpyDeviceToHost, L.stream));
+        if (sums_out) {
+            // blake2sum of all k+m shards while they are on the device (row f2): [s][k+m][32]
+            const uint32_t *d_len = reinterpret_cast<const uint32_t *>(L.d_small);
+            rc = run_sums(ctx, L.d_buf, nullptr, d_len, stride, cnt * k, (int)k, L.d_small + o_sums, nullptr, L.stream,
+                          (int)(k + m), 0);
+            if (rc) return rc;
+            rc = run_sums(ctx, L.d_buf + in_b, nullptr, d_len, stride, cnt * m, (int)m, L.d_small + o_sums, nullptr,
+                          L.stream, (int)(k + m), (int)k);
+            if (rc) return rc;
+            CU_TRY(ctx, cudaMemcpyAsync(sums_out + s0 * (k + m) * 32, L.d_small + o_sums, cnt * (k + m) * 32,
+                                        cudaMemcpyDeviceToHost, L.stream));
+        }
     }
     for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     return GARAGE_EC_OK;

@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "blake2b.h"
 #include "gf256.h"
 
 namespace garage_ec {
@@ -761,6 +762,70 @@ __global__ void fill_random_kernel(unsigned long long *dst, size_t nwords, unsig
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         dst[i] = z ^ (z >> 31);
+    }
+}
+
+// ------------------------------------------------------------------ per-shard integrity (row f2)
+// blake2sum (BLAKE2b-512 truncated to 32 bytes, src/util/data.rs:130-138) of every shard of a
+// batch, one thread per shard.  BLAKE2b is sequential per message, so the parallelism is across
+// the n * shards_per_stripe independent shards; compute-bound (~28 integer instructions per
+// byte), not HBM-bound.  `expect` != NULL turns it into the scrub check: bad[i] = sum differs.
+struct SumParams {
+    const uint8_t *base;        // shard i at base + i * stride
+    const uint32_t *shard_len;  // per stripe, nullable (=> stride)
+    const uint8_t *expect;      // nullable: 32 bytes per shard to compare with
+    uint8_t *sums;              // nullable: 32 bytes per shard out
+    uint8_t *bad;               // nullable: 1 byte per shard out (only with expect)
+    uint32_t stride;
+    uint32_t per_stripe;        // shards per stripe (k, m or k+m)
+    uint32_t n_shards;
+    uint32_t out_per_stripe;    // sums/expect/bad are indexed (i / per_stripe) * out_per_stripe
+    uint32_t out_off;           //                              + out_off + i % per_stripe
+};
+
+__global__ void __launch_bounds__(128) blake2sum_shards_kernel(const __grid_constant__ SumParams q)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n_shards) return;
+    const uint32_t len = q.shard_len ? __ldg(q.shard_len + i / q.per_stripe) : q.stride;
+    const uint8_t *p = q.base + (size_t)i * q.stride;
+    Blake2bState S;
+    blake2b_init512(S);
+    uint64_t m[16];
+    uint32_t off = 0;
+    while (len - off > 128) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + off + 16 * w);
+            m[2 * w] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+            m[2 * w + 1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        }
+        S.t += 128;
+        blake2b_compress(S, m, false);
+        off += 128;
+    }
+    const uint32_t rem = len - off;  // 0..128 bytes in the last block (0 only for an empty shard)
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((uint32_t)(16 * w) < rem) {
+            v = *reinterpret_cast<const uint4 *>(p + off + 16 * w);  // within roundup16(len): readable
+            if (rem - 16 * w < 16) v = mask_tail(v, rem - 16 * w);
+        }
+        m[2 * w] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+        m[2 * w + 1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    }
+    S.t += rem;
+    blake2b_compress(S, m, true);
+    const size_t oi = (size_t)(i / q.per_stripe) * q.out_per_stripe + q.out_off + i % q.per_stripe;
+    if (q.sums) {
+        uint4 *o = reinterpret_cast<uint4 *>(q.sums + oi * 32);
+        o[0] = make_uint4((uint32_t)S.h[0], (uint32_t)(S.h[0] >> 32), (uint32_t)S.h[1], (uint32_t)(S.h[1] >> 32));
+        o[1] = make_uint4((uint32_t)S.h[2], (uint32_t)(S.h[2] >> 32), (uint32_t)S.h[3], (uint32_t)(S.h[3] >> 32));
+    }
+    if (q.expect && q.bad) {
+        const unsigned long long *e = reinterpret_cast<const unsigned long long *>(q.expect + oi * 32);
+        q.bad[oi] = (e[0] != S.h[0]) | (e[1] != S.h[1]) | (e[2] != S.h[2]) | (e[3] != S.h[3]);
     }
 }
 

@@ -125,6 +125,24 @@ int garage_ec_verify(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismat
                      const uint32_t *shard_len, size_t stride, size_t n_stripes, int mem_kind,
                      void *cuda_stream);
 
+/* ---- PER-SHARD INTEGRITY -- call sites: DataBlock::verify,
+ * src/block/block.rs:69-83 (Plain => blake2sum(data) == hash) and read_block_from,
+ * src/block/manager.rs:577-609.  A node stores 1/k of a block, so the whole-block hash cannot be
+ * checked locally: every shard carries its own blake2sum (BLAKE2b-512 truncated to 32 bytes,
+ * src/util/data.rs:130-138), computed here over [0, shard_len) of each shard.
+ *   shards          : n_stripes * shards_per_stripe shards, `stride` apart (shard layout)
+ *   shards_per_stripe: k (a data array), m (a parity array) or k+m
+ *   sums_out        : 32 bytes per shard
+ * garage_ec_check_sums compares with `expect` instead: bad_out[i] = 1 iff shard i differs.     */
+int garage_ec_shard_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint32_t *shard_len,
+                         size_t stride, size_t n_stripes, int shards_per_stripe, uint8_t *sums_out,
+                         int mem_kind, void *cuda_stream);
+int garage_ec_check_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *expect,
+                         const uint32_t *shard_len, size_t stride, size_t n_stripes,
+                         int shards_per_stripe, uint8_t *bad_out, int mem_kind, void *cuda_stream);
+/* host-side blake2sum of one buffer (the same function, for block hashes / small inputs)       */
+void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]);
+
 /* ---- BLOCK-LEVEL convenience (host memory only) -----------------------------------------
  * What rpc_put_block hands over is a contiguous block (bytes::Bytes), not shards.  These do
  * the framing (split + zero pad, src/api/s3/put.rs:583-617 block sizes) on the way to the
@@ -138,6 +156,11 @@ int garage_ec_verify(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismat
 int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks,
                             const uint32_t *block_len, size_t n_blocks, uint8_t *parity_out,
                             size_t stride);
+/* same, and also returns the blake2sum of every shard (k data then m parity per block,
+ * sums_out = n * (k+m) * 32 bytes), computed while the shards are on the device (row f2).   */
+int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *blocks,
+                                      const uint32_t *block_len, size_t n_blocks,
+                                      uint8_t *parity_out, uint8_t *sums_out, size_t stride);
 /* inverse for GET: shards (host, shard layout) + present -> blocks_out[s] (block_len[s]
  * bytes each).  Runs reconstruct only for stripes with an absent data shard.               */
 int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *present,

@@ -24,7 +24,7 @@ def _has_cuda():
 def header_decls():
     src = open(os.path.join(ROOT, "include", "garage_ec.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(garage_ec_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(garage_ec_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_and_binding_agree():
@@ -36,7 +36,7 @@ def test_library_loads_and_exports_every_symbol():
     for name in header_decls():
         assert hasattr(L, name), name
     out = subprocess.run(["nm", "-D", "--defined-only", G.lib_path()], capture_output=True, text=True).stdout
-    exported = set(re.findall(r"\bT (garage_ec_[a-z_]+)", out))
+    exported = set(re.findall(r"\bT (garage_ec_[a-z0-9_]+)", out))
     assert set(header_decls()) <= exported
     assert L.garage_ec_abi_version() == 1
 

@@ -1,0 +1,207 @@
+"""The C++ mirror of BlockManager (libgarage_block.so) driven the way the reference's own tests
+drive the block path: PUT objects of several sizes, GET them back and compare bytes
+(src/garage/tests/s3/multipart.rs, script/test-smoke.sh:51-58), plus what erasure coding adds:
+lost nodes, corrupt shards, resync of a wiped node, scrub."""
+import hashlib
+import os
+import re
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import oracle_lib as O  # noqa: E402
+
+from garage_b200 import block_manager as BM  # noqa: E402
+
+
+# ---------------------------------------------------------------- CPU-only boundary checks
+def test_library_exports_every_declared_symbol():
+    BM.load_library()
+    src = open(os.path.join(ROOT, "include", "garage_block_manager.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decl = sorted(set(re.findall(r"\b(garage_bm_[a-z0-9_]+)\s*\(", src)))
+    assert decl == sorted(BM.SYMBOLS)
+    from garage_b200 import _build
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _build.BM_SO], capture_output=True, text=True).stdout
+    assert set(decl) <= set(re.findall(r"\bT (garage_bm_[a-z0-9_]+)", out))
+    # the host mirror reaches the GPU only through the C ABI: no CUDA runtime symbols of its own
+    und = subprocess.run(["nm", "-D", "--undefined-only", _build.BM_SO], capture_output=True, text=True).stdout
+    assert "garage_ec_encode_blocks_with_sums" in und and "cudaMalloc" not in und and "cudaLaunch" not in und
+
+
+def test_blake2sum_is_garages_content_hash():
+    for n in (0, 1, 3072, 3073, 1 << 20):
+        b = O.fill_random(n, n + 1)
+        assert BM.blake2sum(b) == hashlib.blake2b(b.tobytes()).digest()[:32]  # util/data.rs:130-138
+
+
+def _no_cuda():
+    import torch
+
+    return not torch.cuda.is_available()
+
+
+@pytest.mark.skipif(not _no_cuda(), reason="checks the no-GPU behaviour")
+def test_no_gpu_no_block_manager():
+    with pytest.raises(BM.BlockManagerError) as e:
+        BM.BlockManager(4, 2)
+    assert e.value.code == -5  # GARAGE_EC_E_NODEVICE: no CPU fallback
+
+
+# ---------------------------------------------------------------- GPU: behaviour
+SIZES = [3073, 65536, 1 << 20, (1 << 20) - 1, 5, 777777, 1048575, 4096]  # > INLINE_THRESHOLD (manager.rs:46) except 5
+
+
+def put_all(bm, blocks):
+    hashes = []
+    for b in blocks:
+        h = BM.blake2sum(b)  # put.rs:448
+        assert bm.rpc_put_block(h, b) == BM.OK
+        hashes.append(h)
+    return hashes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,m", [(4, 2), (10, 4), (6, 3)])
+def test_put_get_roundtrip(k, m):
+    blocks = [O.fill_random(n, 100 + i) for i, n in enumerate(SIZES)]
+    with BM.BlockManager(k, m) as bm:
+        hashes = put_all(bm, blocks)
+        for h, b in zip(hashes, blocks):
+            rc, got = bm.rpc_get_block(h)
+            assert rc == BM.OK and np.array_equal(got, b)
+            who = bm.storage_nodes_of(h)
+            assert sorted(who) == list(range(k + m))
+            assert [bm.node_shard_index(who[i], h) for i in range(k + m)] == list(range(k + m))
+        assert bm.metrics()["reconstruct_calls"] == 0  # all data shards present: no GPU on GET
+        rc, _ = bm.rpc_get_block(BM.blake2sum(b"never stored"))
+        assert rc == BM.E_MISSING_BLOCK
+
+
+@pytest.mark.gpu
+def test_get_survives_m_lost_nodes_and_reports_missing_beyond():
+    k, m = 10, 4
+    blocks = [O.fill_random(n, 7 + i) for i, n in enumerate(SIZES)]
+    with BM.BlockManager(k, m, n_nodes=16) as bm:
+        hashes = put_all(bm, blocks)
+        for dead in ([0, 1, 2, 3], [15, 7, 9, 12], [5]):
+            for d in dead:
+                bm.set_node_up(d, False)
+            for h, b in zip(hashes, blocks):
+                rc, got = bm.rpc_get_block(h)
+                assert rc == BM.OK and np.array_equal(got, b), dead
+            for d in dead:
+                bm.set_node_up(d, True)
+        assert bm.metrics()["reconstruct_calls"] > 0
+        for d in range(5):
+            bm.set_node_up(d, False)
+        lost = 0
+        for h in hashes:
+            who = bm.storage_nodes_of(h)
+            down = sum(1 for w in who if w < 5)
+            rc, _ = bm.rpc_get_block(h)
+            assert rc == (BM.E_MISSING_BLOCK if down > m else BM.OK)
+            lost += rc != BM.OK
+        assert lost > 0
+
+
+@pytest.mark.gpu
+def test_put_quorum():
+    k, m = 4, 2
+    b = O.fill_random(200000, 1)
+    with BM.BlockManager(k, m) as bm:
+        bm.set_node_up(0, False)
+        assert bm.rpc_put_block(BM.blake2sum(b), b) == BM.OK  # 5 of 6 stored >= k+1
+        bm.set_node_up(1, False)
+        b2 = O.fill_random(200000, 2)
+        assert bm.rpc_put_block(BM.blake2sum(b2), b2) == BM.E_QUORUM  # 4 < k+1
+
+
+@pytest.mark.gpu
+def test_corrupt_shard_is_quarantined_then_resynced():
+    k, m = 6, 3
+    b = O.fill_random(1 << 20, 3)
+    with BM.BlockManager(k, m) as bm:
+        h = BM.blake2sum(b)
+        assert bm.rpc_put_block(h, b) == BM.OK
+        who = bm.storage_nodes_of(h)
+        assert bm.corrupt_shard(who[2], h, 12345) == BM.OK   # a data shard
+        assert bm.corrupt_shard(who[7], h, 1) == BM.OK       # a parity shard (not read while data is complete)
+        rc, got = bm.rpc_get_block(h)                        # read_block_from: mismatch -> quarantine + resync queue
+        assert rc == BM.OK and np.array_equal(got, b)
+        mt = bm.metrics()
+        assert mt["corruption_counter"] == 1 and mt["resync_queue_length"] == 1
+        assert bm.node_shard_index(who[2], h) == -1
+        failed, done = bm.resync_all(who[2])
+        assert (failed, done) == (0, 1) and bm.node_shard_index(who[2], h) == 2
+        # scrub finds the parity corruption the GET never touched
+        rc, checked, corrupt = bm.scrub(who[7])
+        assert rc == BM.OK and checked == 1 and corrupt == 1
+        assert bm.resync_all(who[7]) == (0, 1)
+        for n in who:
+            rc, checked, corrupt = bm.scrub(n)
+            assert (rc, corrupt) == (BM.OK, 0)
+        rc, got = bm.rpc_get_block(h)
+        assert rc == BM.OK and np.array_equal(got, b)
+
+
+@pytest.mark.gpu
+def test_wiped_node_is_rebuilt_by_repair_and_resync_workers():
+    """`garage repair blocks` on a replaced node (doc/book/operations/durability-repairs.md): every
+    shard it should hold is re-created from k survivors; 8 workers share the GPU through the batcher."""
+    k, m, nblocks = 10, 4, 96
+    rng = np.random.default_rng(0)
+    blocks = [O.fill_random(int(rng.integers(3073, (1 << 20) + 1)), 50 + i) for i in range(nblocks)]
+    with BM.BlockManager(k, m, batch_max_blocks=32, batch_linger_us=2000) as bm:
+        hashes = put_all(bm, blocks)
+        victim = 3
+        before = {h: bm.node_shard_index(victim, h) for h in hashes}
+        for h in hashes:
+            assert bm.drop_shard(victim, h) == BM.OK
+        assert bm.repair_enqueue_missing(victim) == nblocks
+        failed, done = bm.resync_all(victim, workers=8)
+        assert (failed, done) == (0, nblocks)
+        mt = bm.metrics()
+        assert mt["resync_counter"] == nblocks and mt["reconstruct_calls"] == nblocks
+        assert mt["reconstruct_batches"] < nblocks  # calls were coalesced into GPU batches (row f1)
+        assert {h: bm.node_shard_index(victim, h) for h in hashes} == before
+        rc, checked, corrupt = bm.scrub(victim)      # rebuilt shards carry correct per-shard sums
+        assert (rc, checked, corrupt) == (BM.OK, nblocks, 0)
+        # and they are the right bytes: lose m OTHER nodes, so the rebuilt shard is needed to decode
+        for d in (0, 1, 2, 4):
+            bm.set_node_up(d, False)
+        for h, b in zip(hashes, blocks):
+            rc, got = bm.rpc_get_block(h)
+            assert rc == BM.OK and np.array_equal(got, b)
+
+
+@pytest.mark.gpu
+def test_concurrent_puts_are_batched():
+    k, m, per, nthreads = 10, 4, 12, 8
+    blocks = [[O.fill_random(1 << 20, 1000 + t * per + i) for i in range(per)] for t in range(nthreads)]
+    with BM.BlockManager(k, m, batch_max_blocks=64, batch_linger_us=3000) as bm:
+        errs = []
+
+        def worker(t):
+            for b in blocks[t]:
+                if bm.rpc_put_block(BM.blake2sum(b), b) != BM.OK:
+                    errs.append(t)
+
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        assert not errs
+        mt = bm.metrics()
+        assert mt["put_calls"] == per * nthreads and mt["put_batches"] < mt["put_calls"]
+        for t in range(nthreads):
+            for b in blocks[t]:
+                rc, got = bm.rpc_get_block(BM.blake2sum(b))
+                assert rc == BM.OK and np.array_equal(got, b)
