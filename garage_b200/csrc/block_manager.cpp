@@ -372,9 +372,12 @@ struct garage_bm {
                 count++;
             }
         };
+        // data shards first (a complete set needs no GPU), then only as many parity shards as
+        // it takes to reach k -- the reference likewise stops at the first good copy
+        // (manager.rs:292-334); RpcHelper::try_call_many with quorum k is the real-cluster form
+        (void)data_first_only;
         for (int i = 0; i < k; i++) try_shard(i);
-        if (data_first_only && count == k) return count;
-        for (int i = k; i < tot && count < tot; i++) try_shard(i);
+        for (int i = k; i < tot && count < k; i++) try_shard(i);
         return count;
     }
 
