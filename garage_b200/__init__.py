@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "garage_ec_fill_random", "garage_ec_host_alloc", "garage_ec_host_free",
     "garage_ec_launch_count", "garage_ec_set_timing", "garage_ec_timing_read",
     "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
-    "garage_ec_encode_blocks_with_sums",
+    "garage_ec_encode_blocks_with_sums", "garage_ec_scrub_repair",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library(build=True):
     L.garage_ec_verify.argtypes = [vp, vp, vp, vp, sz, sz, i32, vp]
     L.garage_ec_encode_blocks.argtypes = [vp, vp, vp, sz, vp, sz]
     L.garage_ec_encode_blocks_with_sums.argtypes = [vp, vp, vp, sz, vp, vp, sz]
+    L.garage_ec_scrub_repair.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz, i32, vp]
     L.garage_ec_shard_sums.argtypes = [vp, vp, vp, sz, sz, i32, vp, i32, vp]
     L.garage_ec_check_sums.argtypes = [vp, vp, vp, vp, sz, sz, i32, vp, i32, vp]
     L.garage_ec_blake2sum.argtypes = [vp, sz, vp]
@@ -236,6 +237,13 @@ class GarageEc:
         kind, st = self._stream(shards)
         return self._check(self._L.garage_ec_check_sums(self._h, _ptr(shards), _ptr(expect), _ptr(shard_len),
                                                         stride, n, per_stripe, _ptr(bad_out), kind, st))
+
+    def scrub_repair(self, shards, expect_sums, bad_out, stride, n, status=None, shard_len=None):
+        """config-5 sweep: hash every shard, rebuild the corrupt ones in place."""
+        kind, st = self._stream(shards)
+        return self._check(self._L.garage_ec_scrub_repair(self._h, _ptr(shards), _ptr(expect_sums), _ptr(bad_out),
+                                                          _ptr(status), _ptr(shard_len), stride, n, kind, st),
+                           (E_UNRECOVERABLE,))
 
     # -- block-level host API
     def encode_blocks(self, blocks, parity_out, stride, sums_out=None):

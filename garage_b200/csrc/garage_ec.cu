@@ -210,7 +210,7 @@ int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pit
 // Device-resident reconstruct.  plan/counter scratch supplied by the caller (device).
 int run_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present, const uint8_t *want,
                     int32_t *status, const uint32_t *shard_len, size_t stride, size_t n,
-                    StripePlan *plan, uint32_t *counter, cudaStream_t st)
+                    StripePlan *plan, uint32_t *counter, cudaStream_t st, bool present_is_bad = false)
 {
     PlanParams q;
     memset(&q, 0, sizeof(q));
@@ -222,6 +222,7 @@ int run_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
     q.n = (uint32_t)n;
     q.k = (uint32_t)ctx->k;
     q.m = (uint32_t)ctx->m;
+    q.present_is_bad = present_is_bad ? 1u : 0u;
     memcpy(q.P, ctx->P, (size_t)ctx->k * ctx->m);
     const unsigned blocks = (unsigned)((n + kPlanWarps - 1) / kPlanWarps);
     rs_plan_kernel<<<blocks, kPlanWarps * 32, 0, st>>>(q);
@@ -855,6 +856,115 @@ int garage_ec_check_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_
 }
 
 void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]) { blake2sum_host(data, len, out32); }
+
+// --------------------------------------------------------------------------- SCRUB + REPAIR
+int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *expect_sums, uint8_t *bad_out,
+                           int32_t *status, const uint32_t *shard_len, size_t stride, size_t n_stripes, int mem_kind,
+                           void *cuda_stream)
+{
+    if (!ctx || (mem_kind != GARAGE_EC_MEM_HOST && mem_kind != GARAGE_EC_MEM_DEVICE)) return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_stripes, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_stripes == 0) return GARAGE_EC_OK;
+    if (!shards || !expect_sums || !bad_out) return GARAGE_EC_E_INVALID;
+    if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
+    const size_t k = ctx->k, tot = ctx->k + ctx->m;
+    if (n_stripes * tot > 0xffffffffull) return GARAGE_EC_E_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mem_kind == GARAGE_EC_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)cuda_stream;
+        rc = run_sums(ctx, shards, expect_sums, shard_len, stride, n_stripes * tot, (int)tot, nullptr, bad_out, st);
+        if (rc) return rc;
+        void *scratch = nullptr;
+        CU_TRY(ctx, cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
+        StripePlan *plan = reinterpret_cast<StripePlan *>(scratch);
+        uint32_t *counter =
+            reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scratch) + n_stripes * sizeof(StripePlan));
+        rc = run_reconstruct(ctx, shards, bad_out, nullptr, status, shard_len, stride, n_stripes, plan, counter, st,
+                             /*present_is_bad=*/true);
+        cudaError_t e = cudaFreeAsync(scratch, st);
+        if (rc) return rc;
+        if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFreeAsync");
+        return GARAGE_EC_OK;
+    }
+    // HOST: every shard goes up (it has to be hashed); only the rebuilt shards come back.  The
+    // rebuilt set is known once the bad flags are on the host, so each lane's chunk is finished
+    // (flags read, copies issued) when the lane comes round again.
+    std::lock_guard<std::mutex> g(ctx->host_mu);
+    size_t cs = kHostChunkBytes / (tot * stride);
+    if (cs < 1) cs = 1;
+    if (cs > n_stripes) cs = n_stripes;
+    const size_t o_exp = 0, o_bad = o_exp + cs * tot * 32, o_status = o_bad + align_up(cs * tot, 16);
+    const size_t o_len = o_status + align_up(cs * 4, 16), o_plan = o_len + align_up(cs * 4, 16);
+    const size_t small = o_plan + plan_scratch_bytes(cs);
+    for (HostLane &L : ctx->lanes) {
+        rc = lane_reserve(ctx, L, cs * tot * stride, small);
+        if (rc) return rc;
+    }
+    std::vector<int32_t> st_host(status ? 0 : n_stripes);
+    int32_t *st_out = status ? status : st_host.data();
+    struct Pending {
+        bool active = false;
+        size_t s0 = 0, cnt = 0;
+    } pend[kHostLanes];
+    CopyBatch down;
+    auto finish = [&](size_t lane_i) -> int {
+        Pending &P = pend[lane_i];
+        if (!P.active) return GARAGE_EC_OK;
+        HostLane &L = ctx->lanes[lane_i];
+        CU_TRY(ctx, cudaStreamSynchronize(L.stream));  // bad flags + status of this chunk are on the host
+        for (size_t s = P.s0; s < P.s0 + P.cnt; s++) {
+            if (st_out[s] != 0) continue;
+            const size_t len = shard_len ? shard_len[s] : stride;
+            for (size_t i = 0; i < tot; i++)
+                if (bad_out[s * tot + i])
+                    down.add(shards + (s * tot + i) * stride, L.d_buf + ((s - P.s0) * tot + i) * stride,
+                             align_up(len, 16));
+        }
+        int r = down.flush(ctx, cudaMemcpyDeviceToHost, L.stream);
+        P.active = false;
+        return r;
+    };
+    size_t c = 0;
+    for (size_t s0 = 0; s0 < n_stripes; s0 += cs, c++) {
+        const size_t lane_i = c % kHostLanes;
+        HostLane &L = ctx->lanes[lane_i];
+        rc = finish(lane_i);
+        if (rc) return rc;
+        const size_t cnt = n_stripes - s0 < cs ? n_stripes - s0 : cs;
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, shards + s0 * tot * stride, cnt * tot * stride, cudaMemcpyHostToDevice,
+                                    L.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_exp, expect_sums + s0 * tot * 32, cnt * tot * 32,
+                                    cudaMemcpyHostToDevice, L.stream));
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_len, shard_len + s0, cnt * 4, cudaMemcpyHostToDevice, L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small + o_len);
+        }
+        rc = run_sums(ctx, L.d_buf, L.d_small + o_exp, d_len, stride, cnt * tot, (int)tot, nullptr, L.d_small + o_bad,
+                      L.stream);
+        if (rc) return rc;
+        StripePlan *d_plan = reinterpret_cast<StripePlan *>(L.d_small + o_plan);
+        uint32_t *d_counter = reinterpret_cast<uint32_t *>(L.d_small + o_plan + cnt * sizeof(StripePlan));
+        rc = run_reconstruct(ctx, L.d_buf, L.d_small + o_bad, nullptr, reinterpret_cast<int32_t *>(L.d_small + o_status),
+                             d_len, stride, cnt, d_plan, d_counter, L.stream, true);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpyAsync(bad_out + s0 * tot, L.d_small + o_bad, cnt * tot, cudaMemcpyDeviceToHost, L.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(st_out + s0, L.d_small + o_status, cnt * 4, cudaMemcpyDeviceToHost, L.stream));
+        pend[lane_i].active = true;
+        pend[lane_i].s0 = s0;
+        pend[lane_i].cnt = cnt;
+    }
+    for (size_t l = 0; l < (size_t)kHostLanes; l++) {
+        rc = finish(l);
+        if (rc) return rc;
+    }
+    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    (void)k;
+    for (size_t s = 0; s < n_stripes; s++)
+        if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
+    return GARAGE_EC_OK;
+}
 
 // --------------------------------------------------------------------------- BLOCK-LEVEL
 // H2D of one block split into k zero-padded shards at dst (device, shard layout).

@@ -622,6 +622,7 @@ struct PlanParams {
     StripePlan *plan;        // n
     uint32_t *counter;       // reset to 0 for the apply kernel's scheduler
     uint32_t n, k, m;
+    uint32_t present_is_bad;  // 1: `present` holds "bad" flags (scrub): a shard is present iff flag == 0
     uint8_t P[kMaxM * kMaxK];  // parity rows, P[i*k + j]
 };
 
@@ -654,8 +655,9 @@ __global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_c
     const uint8_t *wn = q.want ? q.want + (size_t)s * tot : nullptr;
 
     // presence / wanted masks (tot <= 40: two ballot rounds)
-    const bool p0 = lane < tot && pr[lane] != 0;
-    const bool p1 = lane + 32 < tot && pr[lane + 32] != 0;
+    const bool inv = q.present_is_bad != 0;
+    const bool p0 = lane < tot && ((pr[lane] != 0) != inv);
+    const bool p1 = lane + 32 < tot && ((pr[lane + 32] != 0) != inv);
     const unsigned long long present =
         (unsigned long long)__ballot_sync(0xffffffffu, p0) |
         ((unsigned long long)__ballot_sync(0xffffffffu, p1) << 32);

@@ -140,6 +140,14 @@ int garage_ec_shard_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint32
 int garage_ec_check_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *expect,
                          const uint32_t *shard_len, size_t stride, size_t n_stripes,
                          int shards_per_stripe, uint8_t *bad_out, int mem_kind, void *cuda_stream);
+/* ---- SCRUB + REPAIR sweep (BASELINE config 5) -- ScrubWorker::work (src/block/repair.rs:438-490)
+ * feeding resync (src/block/resync.rs:354-503) in one pass: blake2sum every shard, treat the ones
+ * whose sum differs from `expect_sums` as erased, rebuild them in place from the first k intact
+ * shards.  bad_out[s*(k+m)+i] = 1 iff shard i was corrupt; status[s] = 0 or
+ * GARAGE_EC_E_UNRECOVERABLE (> m corrupt shards: reported, never fatal -- resync.rs:300-315).     */
+int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *expect_sums,
+                           uint8_t *bad_out, int32_t *status, const uint32_t *shard_len,
+                           size_t stride, size_t n_stripes, int mem_kind, void *cuda_stream);
 /* host-side blake2sum of one buffer (the same function, for block hashes / small inputs)       */
 void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]);
 
