@@ -119,15 +119,15 @@ struct TimedLaunch {
 template <int MODE, int K> struct LaunchShape {
     static constexpr int NT = (GEC_NT_ENC != 512) ? GEC_NT_ENC
                               : (K == 0 ? 512 : (K <= 4 ? 1024 : (K <= 6 ? 768 : (K <= 8 ? 640 : 512))));
-    static constexpr bool PIPE = GEC_PIPE_ENC;
+    static constexpr bool PIPE = GEC_PIPE_ENC && slots_for_k(K > 0 ? K : 1) <= 12;  // 2 x slots x 4 registers
 };
 template <int K> struct LaunchShape<kModePlan, K> {
     static constexpr int NT = (GEC_NT_PLAN != 512) ? GEC_NT_PLAN
                               : (K == 0 ? 512 : (K <= 4 ? 1024 : (K <= 6 ? 768 : (K <= 8 ? 640 : 512))));
-    static constexpr bool PIPE = GEC_PIPE_PLAN;
+    static constexpr bool PIPE = GEC_PIPE_PLAN && slots_for_k(K > 0 ? K : 1) <= 12;
 };
 template <int K> struct LaunchShape<kModeVerify, K> {
-    static constexpr int NT = GEC_NT_VER;
+    static constexpr int NT = (GEC_NT_VER != 1024) ? GEC_NT_VER : ((K == 0 || K > 11) ? 512 : 1024);
     static constexpr bool PIPE = GEC_PIPE_VER || (K > 0 && K <= 4);
 };
 
@@ -155,13 +155,10 @@ cudaError_t launch_apply(garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t 
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     switch (p.k) {
 #ifndef GEC_FAST_BUILD
-    case 2: return launch_apply_t<2, MODE>(ctx, p, st);
-    case 3: return launch_apply_t<3, MODE>(ctx, p, st);
-    case 4: return launch_apply_t<4, MODE>(ctx, p, st);
-    case 5: return launch_apply_t<5, MODE>(ctx, p, st);
-    case 6: return launch_apply_t<6, MODE>(ctx, p, st);
-    case 8: return launch_apply_t<8, MODE>(ctx, p, st);
-    case 12: return launch_apply_t<12, MODE>(ctx, p, st);
+#define GEC_CASE(KK) case KK: return launch_apply_t<KK, MODE>(ctx, p, st);
+        GEC_CASE(1) GEC_CASE(2) GEC_CASE(3) GEC_CASE(4) GEC_CASE(5) GEC_CASE(6) GEC_CASE(7) GEC_CASE(8)
+        GEC_CASE(9) GEC_CASE(11) GEC_CASE(12) GEC_CASE(13) GEC_CASE(14) GEC_CASE(15) GEC_CASE(16)
+#undef GEC_CASE
 #endif
     case 10: return launch_apply_t<10, MODE>(ctx, p, st);
     default: return launch_apply_t<0, MODE>(ctx, p, st);

@@ -68,10 +68,12 @@ constexpr int kMaxM = 8;
 constexpr int kRowsPerPass = 4;  // output rows packed in one 32-bit table word
 constexpr uint32_t kGroupBytes = 32768;  // one table group: 256 rows x 32 banks x 4 B
 
-// tables per 32 KB group for k sources: smallest G (least padding) whose groups fit 227 KB
+// tables per 32 KB group for k sources: smallest G (least padding) whose groups need <= 192 KB,
+// so that >= 32 KB of the SM's 228 KB stay L1 (with 224 KB of tables the global loads starve:
+// k = 7 measured 0.65 of peak against 0.92 for k = 6)
 __host__ __device__ constexpr int log2_group_for_k(int k)
 {
-    return k <= 7 ? 0 : (k <= 14 ? 1 : (k <= 28 ? 2 : 3));
+    return k <= 6 ? 0 : (k <= 12 ? 1 : (k <= 24 ? 2 : 3));
 }
 __host__ __device__ constexpr int slots_for_k(int k)
 {
