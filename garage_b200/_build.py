@@ -38,16 +38,38 @@ def stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def _multi_rank():
+    return int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+
+def _wait_for(path, seconds=600):
+    import time
+
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > seconds:
+            raise RuntimeError("timed out waiting for %s to be built by local rank 0" % path)
+        time.sleep(0.5)
+    return path
+
+
 def build(force=False, verbose=False):
-    """Compile the CUDA extension if sources are newer than the .so (or force)."""
-    if not force and not stale():
-        return SO
+    """Compile the CUDA extension if sources are newer than the .so (or force).  Under
+    torchrun only local rank 0 ever compiles, and only when the library is missing (a stale
+    mtime after the snapshot copy must not make 8 ranks race on one output file)."""
+    if not force:
+        if os.path.exists(SO) and (_multi_rank() or not stale()):
+            return SO
+        if _multi_rank() and int(os.environ.get("LOCAL_RANK", "0")) != 0:
+            return _wait_for(SO)
     if not all(os.path.exists(os.path.join(CSRC, d)) for d in DEPS):
         raise RuntimeError("garage_b200/csrc sources missing")
-    cmd = nvcc_cmd(extra=("-Xptxas", "-v") if verbose else ())
+    tmp = SO + ".tmp%d" % os.getpid()
+    cmd = nvcc_cmd(out=tmp, extra=("-Xptxas", "-v") if verbose else ())
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, SO)  # atomic: a concurrent loader never sees a half-written library
     if verbose:
         print(r.stderr)
     return SO
@@ -61,17 +83,21 @@ BM_DEPS = [os.path.join(CSRC, "block_manager.cpp"), os.path.join(ROOT, "include"
 def build_block_manager(force=False):
     """C++ host mirror of BlockManager (libgarage_block.so): plain g++, links only the C ABI."""
     build(force=False)
-    if (not force and os.path.exists(BM_SO)
-            and all(os.path.getmtime(d) <= os.path.getmtime(BM_SO) for d in BM_DEPS if os.path.exists(d))
-            and os.path.getmtime(SO) <= os.path.getmtime(BM_SO)):
-        return BM_SO
+    if not force and os.path.exists(BM_SO):
+        fresh = (all(os.path.getmtime(d) <= os.path.getmtime(BM_SO) for d in BM_DEPS if os.path.exists(d))
+                 and os.path.getmtime(SO) <= os.path.getmtime(BM_SO))
+        if fresh or _multi_rank():
+            return BM_SO
+    if not force and _multi_rank() and int(os.environ.get("LOCAL_RANK", "0")) != 0:
+        return _wait_for(BM_SO)
     cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wall", "-Wextra",
            "-I", os.path.join(ROOT, "include"), BM_DEPS[0], "-L", PKG, "-lgarage_ec",
-           "-Wl,-rpath,$ORIGIN", "-o", BM_SO]
+           "-Wl,-rpath,$ORIGIN", "-o", BM_SO + ".tmp%d" % os.getpid()]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    os.replace(cmd[-1], BM_SO)
     return BM_SO
 
 

@@ -80,8 +80,26 @@ __host__ __device__ constexpr int slots_for_k(int k)
     return ((k + (1 << log2_group_for_k(k)) - 1) >> log2_group_for_k(k)) << log2_group_for_k(k);
 }
 
-__constant__ uint8_t c_gf_exp[512] = GARAGE_EC_GF_EXP_INIT;
-__constant__ uint8_t c_gf_log[256] = GARAGE_EC_GF_LOG_INIT;
+// GF(2^8) antilog / log tables, pinned in constant memory.  Kernels that need general products
+// (decode planning) stage them into shared memory with warp-UNIFORM 16-byte constant loads:
+// a per-lane byte index into __constant__ memory serialises 32-way in the constant cache (the
+// first version of rs_plan_kernel spent 30 of its 40 us there).
+struct GfTables {
+    uint8_t exp[512];
+    uint8_t log[256];
+};
+__constant__ __align__(16) GfTables c_gf = {GARAGE_EC_GF_EXP_INIT, GARAGE_EC_GF_LOG_INIT};
+
+__device__ __forceinline__ void stage_gf_tables(uint8_t *s_gf /* 768 B, 16-byte aligned */)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(&c_gf);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t i = warp; i < sizeof(GfTables) / 16; i += nwarps) {
+        const uint4 v = src[i];  // same address in every lane: one constant-cache broadcast
+        if (lane < 4)
+            reinterpret_cast<uint32_t *>(s_gf)[i * 4 + lane] = lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
+    }
+}
 
 enum ApplyMode { kModeEncode = 0, kModePlan = 1, kModeVerify = 2 };
 
@@ -635,14 +653,14 @@ constexpr int kPlanWarps = 4;
 // survivors straight to every wanted absent shard.
 __global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_constant__ PlanParams q)
 {
-    __shared__ uint8_t s_exp[512];
-    __shared__ uint8_t s_log[256];
+    __shared__ __align__(16) uint8_t s_gf[sizeof(GfTables)];
+    uint8_t *const s_exp = s_gf, *const s_log = s_gf + 512;
     __shared__ uint8_t s_A[kPlanWarps][kMaxK][2 * kMaxK];
     __shared__ uint8_t s_surv[kPlanWarps][kMaxK];
     __shared__ uint8_t s_out[kPlanWarps][kMaxM];
+    __shared__ uint8_t s_col[kPlanWarps][kMaxK];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t i = tid; i < 512; i += blockDim.x) s_exp[i] = c_gf_exp[i];
-    for (uint32_t i = tid; i < 256; i += blockDim.x) s_log[i] = c_gf_log[i];
+    stage_gf_tables(s_gf);
     if (blockIdx.x == 0 && tid == 0) *q.counter = 0;
     __syncthreads();
     auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
@@ -728,14 +746,21 @@ __global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_c
             A[c][x] = (uint8_t)mul(a, iv);   // scaled pivot row
         }
         __syncwarp();
+        // eliminate column c from every other row: lanes own columns; the k row factors are
+        // copied out of column c first (lane c is about to overwrite it)
+        const uint32_t p0v = lane < 2 * k ? A[c][lane] : 0, p1v = lane + 32 < 2 * k ? A[c][lane + 32] : 0;
+        const uint32_t lp0 = s_log[p0v], lp1 = s_log[p1v];
+        if (lane < k) s_col[warp][lane] = lane == c ? 0 : A[lane][c];
+        __syncwarp();
         for (uint32_t r = 0; r < k; r++) {
-            if (r == c) continue;
-            const uint32_t f = A[r][c];
-            __syncwarp();
-            if (f)
-                for (uint32_t x = lane; x < 2 * k; x += 32) A[r][x] ^= (uint8_t)mul(f, A[c][x]);
-            __syncwarp();
+            const uint32_t f = s_col[warp][r];  // broadcast
+            if (f) {                            // warp-uniform
+                const uint32_t lf = s_log[f];
+                if (p0v) A[r][lane] ^= s_exp[lf + lp0];
+                if (p1v) A[r][lane + 32] ^= s_exp[lf + lp1];
+            }
         }
+        __syncwarp();
     }
     // inverse now in A[:, k..2k).  Compose rows for the outputs.
     for (int r = 0; r < nrows; r++) {

@@ -17,11 +17,9 @@ _i32p = C.POINTER(C.c_int32)
 
 def build(force=False):
     srcs = [os.path.join(ODIR, f) for f in ("rs_oracle.c", "rs_simd.c", "rs_oracle.h")]
-    if (
-        force
-        or not os.path.exists(SO)
-        or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs)
-    ):
+    multi = int(os.environ.get("WORLD_SIZE", "1")) > 1  # only rank 0 uses the oracle; never race on it
+    stale = os.path.exists(SO) and any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs)
+    if force or not os.path.exists(SO) or (stale and not multi):
         if all(os.path.exists(s) for s in srcs):
             subprocess.run(["make", "-C", ODIR, "-s", "-B"], check=True)
     return SO
