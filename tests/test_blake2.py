@@ -86,3 +86,29 @@ def test_shard_sums_full_size_sample():
         d3 = d.view(n * k, stride)
         for i in (0, 1, 777, n * k - 1):
             assert h[i].tobytes() == ref(d3[i, :L].cpu().numpy()), i
+
+
+@pytest.mark.gpu
+def test_shard_sums_many_small_shards_scalar_kernel():
+    """>= 24 000 shards takes the one-thread-per-shard kernel; fewer takes the quad kernel"""
+    import torch
+
+    k, m, n, stride = 10, 4, 2000, 208
+    tot = k + m
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, stride + 1, n).astype(np.uint32)
+    sh = O.fill_random(n * tot * stride, 9).reshape(n, tot, stride)
+    with G.GarageEc(0, k, m) as ec:
+        d = torch.from_numpy(sh.reshape(-1)).cuda()
+        dl = torch.from_numpy(lens.astype(np.int32)).cuda()
+        sums = torch.zeros(n * tot * 32, dtype=torch.uint8, device="cuda")
+        ec.shard_sums(d, sums, stride, n, tot, shard_len=dl)          # 28 000 shards: scalar kernel
+        h = sums.cpu().numpy().reshape(n, tot, 32)
+        sums2 = torch.zeros(n * k * 32, dtype=torch.uint8, device="cuda")
+        dk = torch.from_numpy(np.ascontiguousarray(sh[:, :k]).reshape(-1)).cuda()
+        ec.shard_sums(dk, sums2, stride, n, k, shard_len=dl)          # 20 000 shards: quad kernel
+        h2 = sums2.cpu().numpy().reshape(n, k, 32)
+        assert np.array_equal(h[:, :k], h2)
+        for s in rng.integers(0, n, 40):
+            for i in (0, 5, 13):
+                assert h[s, i].tobytes() == ref(sh[s, i, : lens[s]]), (s, i)
