@@ -420,8 +420,9 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
     assert ok, "e2e results differ from the device-resident pass"
     res = {
         "value": 2 * n * B * world * steps / el / GIB, "unit": "GiB/s", "steps": steps, "blocks_per_step": n,
-        "h2d_bytes_per_step": int(n * k * stride + n * k * stride + 2 * n * 4 + n * tot),  # encode data + the k survivors
-        "d2h_bytes_per_step": int(n * m * stride + n * m * ((L + 15) // 16 * 16) + n * 4),
+        # whole job (all ranks): encode data + the k survivors up; parity + rebuilt shards + status down
+        "h2d_bytes_per_step": int(world * (n * k * stride + n * k * stride + 2 * n * 4 + n * tot)),
+        "d2h_bytes_per_step": int(world * (n * m * stride + n * m * ((L + 15) // 16 * 16) + n * 4)),
         "api": "garage_ec_encode + garage_ec_reconstruct, GARAGE_EC_MEM_HOST, pinned buffers from garage_ec_host_alloc",
         "timer": "host wall clock around synchronous calls (max over ranks)", "checked": bool(ok),
     }
