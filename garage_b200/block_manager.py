@@ -29,7 +29,8 @@ class Metrics(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "bytes_written", "bytes_read", "corruption_counter", "resync_counter", "resync_error_counter",
         "resync_recv_counter", "delete_counter", "put_calls", "put_batches", "reconstruct_calls",
-        "reconstruct_batches", "scrub_shards_checked", "scrub_corruptions", "resync_queue_length")]
+        "reconstruct_batches", "scrub_shards_checked", "scrub_corruptions", "resync_queue_length",
+        "encode_call_us", "reconstruct_call_us")]
 
 
 _lib = None

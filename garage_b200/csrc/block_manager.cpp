@@ -96,10 +96,13 @@ private:
 template <class Item>
 class Batcher {
 public:
-    using Run = std::function<void(std::vector<Item *> &)>;
-    Batcher(size_t max_items, unsigned linger_us, Run run)
-        : max_(std::max<size_t>(1, max_items)), linger_(linger_us), run_(std::move(run)), th_([this] { loop(); })
+    using Run = std::function<void(int /*worker*/, std::vector<Item *> &)>;
+    // `workers` dispatcher threads pull batches from one queue: while one batch is on the GPU the
+    // next one is being collected / copied (each worker owns a garage_ec context and buffers)
+    Batcher(size_t max_items, unsigned linger_us, int workers, Run run)
+        : max_(std::max<size_t>(1, max_items)), linger_(linger_us), run_(std::move(run))
     {
+        for (int w = 0; w < std::max(1, workers); w++) th_.emplace_back([this, w] { loop(w); });
     }
     ~Batcher()
     {
@@ -108,7 +111,7 @@ public:
             stop_ = true;
         }
         cv_.notify_all();
-        th_.join();
+        for (auto &t : th_) t.join();
     }
     // blocks the calling thread until its item has been processed in some batch
     int submit(Item &it)
@@ -125,7 +128,7 @@ public:
     uint64_t items() const { return items_.load(); }
 
 private:
-    void loop()
+    void loop(int w)
     {
         std::vector<Item *> batch;
         for (;;) {
@@ -144,9 +147,10 @@ private:
                     q_.pop_front();
                 }
             }
+            if (batch.empty()) continue;  // another worker took them
             batches_++;
             items_ += batch.size();
-            run_(batch);  // sets every item's promise
+            run_(w, batch);  // sets every item's promise
         }
     }
     const size_t max_;
@@ -157,7 +161,52 @@ private:
     std::deque<Item *> q_;
     bool stop_ = false;
     std::atomic<uint64_t> batches_{0}, items_{0};
-    std::thread th_;
+    std::vector<std::thread> th_;
+};
+
+// pool of pinned block-sized slots: the calling thread copies its block into a slot (in
+// parallel with every other caller) so the dispatcher's H2D runs at PCIe speed from pinned
+// memory -- in Garage proper the body copy of BytesBuf::take_exact would land here directly
+class SlotPool {
+public:
+    bool init(garage_ec_ctx *ctx, size_t slots, size_t slot_bytes)
+    {
+        ctx_ = ctx;
+        slot_bytes_ = slot_bytes;
+        if (garage_ec_host_alloc(ctx, &base_, slots * slot_bytes) != GARAGE_EC_OK) return false;
+        for (size_t i = 0; i < slots; i++) free_.push_back(static_cast<uint8_t *>(base_) + i * slot_bytes);
+        return true;
+    }
+    uint8_t *acquire()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !free_.empty(); });
+        uint8_t *p = free_.back();
+        free_.pop_back();
+        return p;
+    }
+    void release(uint8_t *p)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            free_.push_back(p);
+        }
+        cv_.notify_one();
+    }
+    size_t slot_bytes() const { return slot_bytes_; }
+    void destroy()
+    {
+        if (base_) garage_ec_host_free(ctx_, base_);
+        base_ = nullptr;
+    }
+
+private:
+    garage_ec_ctx *ctx_ = nullptr;
+    void *base_ = nullptr;
+    size_t slot_bytes_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<uint8_t *> free_;
 };
 
 struct EncodeItem {
@@ -207,7 +256,11 @@ struct PinnedBuf {
 struct garage_bm {
     garage_bm_config cfg{};
     int k = 0, m = 0, tot = 0;
-    garage_ec_ctx *ec = nullptr;
+    static constexpr int kWorkers = 3;  // dispatcher threads per batcher (overlap PCIe / GPU / CPU copies)
+    garage_ec_ctx *ec = nullptr;                 // scrub + geometry helpers
+    garage_ec_ctx *enc_ctx[kWorkers] = {nullptr};  // one context (= one set of staging lanes) per worker
+    garage_ec_ctx *rec_ctx[kWorkers] = {nullptr};
+    SlotPool slots;
     std::vector<std::unique_ptr<Node>> nodes;
     // stands in for the block_ref / rc tables (src/model/s3/block_ref_table.rs, src/block/rc.rs):
     // which blocks exist and how long they are
@@ -216,12 +269,12 @@ struct garage_bm {
     std::unique_ptr<ByteSemaphore> ram;
     std::unique_ptr<Batcher<EncodeItem>> enc_batcher;
     std::unique_ptr<Batcher<ReconItem>> rec_batcher;
-    PinnedBuf enc_parity, rec_buf, scrub_buf;
+    PinnedBuf enc_parity[kWorkers], rec_buf[kWorkers], scrub_buf;
     std::mutex scrub_mu;
     // metrics (src/block/metrics.rs)
     std::atomic<uint64_t> bytes_written{0}, bytes_read{0}, corruption_counter{0}, resync_counter{0},
         resync_error_counter{0}, resync_recv_counter{0}, delete_counter{0}, put_calls{0}, reconstruct_calls{0},
-        scrub_checked{0}, scrub_corrupt{0};
+        scrub_checked{0}, scrub_corrupt{0}, enc_gpu_us{0}, rec_gpu_us{0};
 
     // rpc/layout/version.rs:117-137: top 8 bits of the hash -> partition -> k+m distinct nodes
     void storage_nodes_of(const Hash &h, int *out) const
@@ -283,7 +336,7 @@ struct garage_bm {
     }
 
     // ---- batch runners (dispatcher threads) -------------------------------------------------
-    void run_encode(std::vector<EncodeItem *> &b)
+    void run_encode(int w, std::vector<EncodeItem *> &b)
     {
         const size_t n = b.size();
         uint32_t max_len = 0;
@@ -295,11 +348,13 @@ struct garage_bm {
             max_len = std::max(max_len, b[i]->len);
         }
         const size_t stride = garage_ec_stride_for(garage_ec_shard_len(max_len, k));
-        uint8_t *par = enc_parity.get(n * m * stride + n * tot * 32);
+        uint8_t *par = enc_parity[w].get(n * m * stride + n * tot * 32);
         int rc = par ? GARAGE_EC_OK : GARAGE_EC_E_NOMEM;
         uint8_t *sums = par ? par + n * m * stride : nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         if (rc == GARAGE_EC_OK)
-            rc = garage_ec_encode_blocks_with_sums(ec, ptrs.data(), lens.data(), n, par, sums, stride);
+            rc = garage_ec_encode_blocks_with_sums(enc_ctx[w], ptrs.data(), lens.data(), n, par, sums, stride);
+        enc_gpu_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
         for (size_t i = 0; i < n; i++) {
             if (rc == GARAGE_EC_OK) {
                 const size_t L = garage_ec_shard_len(lens[i], k);
@@ -312,14 +367,14 @@ struct garage_bm {
         }
     }
 
-    void run_reconstruct(std::vector<ReconItem *> &b)
+    void run_reconstruct(int w, std::vector<ReconItem *> &b)
     {
         const size_t n = b.size();
         uint32_t max_len = 0;
         for (auto *it : b) max_len = std::max(max_len, it->block_len);
         const size_t stride = garage_ec_stride_for(garage_ec_shard_len(max_len, k));
         const size_t data_b = n * tot * stride;
-        uint8_t *buf = rec_buf.get(data_b + 2 * n * tot + n * 8);
+        uint8_t *buf = rec_buf[w].get(data_b + 2 * n * tot + n * 8);
         if (!buf) {
             for (auto *it : b) it->done.set_value(GARAGE_EC_E_NOMEM);
             return;
@@ -336,8 +391,10 @@ struct garage_bm {
                 if (b[i]->shard[s]) memcpy(buf + (i * tot + s) * stride, b[i]->shard[s], L);
             }
         }
-        int rc = garage_ec_reconstruct(ec, buf, present, want, status.data(), lens.data(), stride, n,
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = garage_ec_reconstruct(rec_ctx[w], buf, present, want, status.data(), lens.data(), stride, n,
                                        GARAGE_EC_MEM_HOST, nullptr);
+        rec_gpu_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
         for (size_t i = 0; i < n; i++) {
             int r = rc;
             if (rc == GARAGE_EC_OK || rc == GARAGE_EC_E_UNRECOVERABLE) {
@@ -390,10 +447,14 @@ struct garage_bm {
         const uint64_t permits = (uint64_t)len * tot / k;  // manager.rs:380-385, x (k+m)/k for the parity
         ram->acquire(permits);
         put_calls++;
+        // land the block in pinned memory (caller's thread, so copies of concurrent PUTs overlap)
+        uint8_t *slot = len <= slots.slot_bytes() ? slots.acquire() : nullptr;
+        if (slot) memcpy(slot, data, len);
         EncodeItem it;
-        it.data = data;
+        it.data = slot ? slot : data;
         it.len = (uint32_t)len;
         int rc = enc_batcher->submit(it);
+        if (slot) slots.release(slot);
         if (rc != GARAGE_EC_OK) {
             ram->release(permits);
             return rc;
@@ -679,12 +740,27 @@ int garage_bm_create(garage_bm **out, const garage_bm_config *cfg)
     if (rc != GARAGE_EC_OK) return rc;  // no GPU => no block manager: there is no CPU fallback
     for (int i = 0; i < cfg->n_nodes; i++) bm->nodes.emplace_back(new Node());
     bm->ram.reset(new ByteSemaphore(cfg->block_ram_buffer_max ? cfg->block_ram_buffer_max : (256ull << 20)));
-    bm->enc_parity.ctx = bm->rec_buf.ctx = bm->scrub_buf.ctx = bm->ec;
+    bm->scrub_buf.ctx = bm->ec;
+    for (int w = 0; w < garage_bm::kWorkers; w++) {
+        rc = garage_ec_create(&bm->enc_ctx[w], cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
+        if (rc == GARAGE_EC_OK) rc = garage_ec_create(&bm->rec_ctx[w], cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
+        if (rc != GARAGE_EC_OK) {
+            garage_bm_destroy(bm.release());
+            return rc;
+        }
+        bm->enc_parity[w].ctx = bm->enc_ctx[w];
+        bm->rec_buf[w].ctx = bm->rec_ctx[w];
+    }
+    const size_t nslots = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * (garage_bm::kWorkers + 1);
+    if (!bm->slots.init(bm->ec, nslots, cfg->block_size ? cfg->block_size : (1u << 20))) {
+        garage_bm_destroy(bm.release());
+        return GARAGE_EC_E_NOMEM;
+    }
     garage_bm *raw = bm.get();
-    bm->enc_batcher.reset(new Batcher<EncodeItem>(cfg->batch_max_blocks, cfg->batch_linger_us,
-                                                  [raw](std::vector<EncodeItem *> &b) { raw->run_encode(b); }));
-    bm->rec_batcher.reset(new Batcher<ReconItem>(cfg->batch_max_blocks, cfg->batch_linger_us,
-                                                 [raw](std::vector<ReconItem *> &b) { raw->run_reconstruct(b); }));
+    bm->enc_batcher.reset(new Batcher<EncodeItem>(cfg->batch_max_blocks, cfg->batch_linger_us, garage_bm::kWorkers,
+                                                  [raw](int w, std::vector<EncodeItem *> &b) { raw->run_encode(w, b); }));
+    bm->rec_batcher.reset(new Batcher<ReconItem>(cfg->batch_max_blocks, cfg->batch_linger_us, garage_bm::kWorkers,
+                                                 [raw](int w, std::vector<ReconItem *> &b) { raw->run_reconstruct(w, b); }));
     *out = bm.release();
     return GARAGE_BM_OK;
 }
@@ -695,10 +771,18 @@ void garage_bm_destroy(garage_bm *bm)
     bm->enc_batcher.reset();
     bm->rec_batcher.reset();
     garage_ec_ctx *ec = bm->ec;
-    bm->enc_parity.release();  // pinned buffers go before the context
-    bm->rec_buf.release();
+    garage_ec_ctx *ctxs[2 * garage_bm::kWorkers];
+    for (int w = 0; w < garage_bm::kWorkers; w++) {
+        bm->enc_parity[w].release();  // pinned buffers go before their context
+        bm->rec_buf[w].release();
+        ctxs[2 * w] = bm->enc_ctx[w];
+        ctxs[2 * w + 1] = bm->rec_ctx[w];
+    }
     bm->scrub_buf.release();
+    bm->slots.destroy();
     delete bm;
+    for (garage_ec_ctx *c : ctxs)
+        if (c) garage_ec_destroy(c);
     garage_ec_destroy(ec);
 }
 
@@ -810,6 +894,8 @@ void garage_bm_get_metrics(garage_bm *bm, garage_bm_metrics *o)
     o->reconstruct_batches = bm->rec_batcher ? bm->rec_batcher->batches() : 0;
     o->scrub_shards_checked = bm->scrub_checked;
     o->scrub_corruptions = bm->scrub_corrupt;
+    o->encode_call_us = bm->enc_gpu_us;
+    o->reconstruct_call_us = bm->rec_gpu_us;
     uint64_t ql = 0;
     for (auto &n : bm->nodes) {
         std::lock_guard<std::mutex> lk(n->mu);

@@ -756,7 +756,8 @@ int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *pr
 // --------------------------------------------------------------------------- SHARD SUMS
 static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *expect, const uint32_t *shard_len,
                     size_t stride, size_t n_shards, int per_stripe, uint8_t *sums, uint8_t *bad, cudaStream_t st,
-                    int out_per_stripe = 0, int out_off = 0)
+                    int out_per_stripe = 0, int out_off = 0, const uint8_t *shards2 = nullptr, size_t n_shards2 = 0,
+                    int per_stripe2 = 1, int out_off2 = 0)
 {
     SumParams q;
     memset(&q, 0, sizeof(q));
@@ -767,9 +768,14 @@ static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *ex
     q.bad = bad;
     q.stride = (uint32_t)stride;
     q.per_stripe = (uint32_t)per_stripe;
-    q.n_shards = (uint32_t)n_shards;
+    q.n_shards = (uint32_t)(n_shards + n_shards2);
     q.out_per_stripe = (uint32_t)(out_per_stripe ? out_per_stripe : per_stripe);
     q.out_off = (uint32_t)out_off;
+    q.base2 = shards2;
+    q.n_first = (uint32_t)n_shards;
+    q.per_stripe2 = (uint32_t)per_stripe2;
+    q.out_off2 = (uint32_t)out_off2;
+    n_shards += n_shards2;
     // few shards: four lanes per shard (4x the parallelism, but the quad shuffles make it
     // LSU-bound: measured 5.4 ms vs 7.6 ms at 18 432 shards and 6.0 vs 5.7 ms at 28 672);
     // from ~24 000 shards on one thread per shard keeps the schedulers busy enough
@@ -1045,10 +1051,7 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
             // blake2sum of all k+m shards while they are on the device (row f2): [s][k+m][32]
             const uint32_t *d_len = reinterpret_cast<const uint32_t *>(L.d_small);
             rc = run_sums(ctx, L.d_buf, nullptr, d_len, stride, cnt * k, (int)k, L.d_small + o_sums, nullptr, L.stream,
-                          (int)(k + m), 0);
-            if (rc) return rc;
-            rc = run_sums(ctx, L.d_buf + in_b, nullptr, d_len, stride, cnt * m, (int)m, L.d_small + o_sums, nullptr,
-                          L.stream, (int)(k + m), (int)k);
+                          (int)(k + m), 0, L.d_buf + in_b, cnt * m, (int)m, (int)k);
             if (rc) return rc;
             CU_TRY(ctx, cudaMemcpyAsync(sums_out + s0 * (k + m) * 32, L.d_small + o_sums, cnt * (k + m) * 32,
                                         cudaMemcpyDeviceToHost, L.stream));

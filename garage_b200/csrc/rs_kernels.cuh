@@ -810,14 +810,40 @@ struct SumParams {
     uint32_t n_shards;
     uint32_t out_per_stripe;    // sums/expect/bad are indexed (i / per_stripe) * out_per_stripe
     uint32_t out_off;           //                              + out_off + i % per_stripe
+    // optional second segment (shards n_first.. of the launch): lets one launch hash the data
+    // array AND the parity array of an encode batch (half the latency of two launches)
+    const uint8_t *base2;
+    uint32_t n_first;           // shards in the first segment (== n_shards when there is no second)
+    uint32_t per_stripe2;
+    uint32_t out_off2;
 };
+
+// where shard i of a launch lives, which stripe's length applies, and its slot in sums/expect/bad
+__device__ __forceinline__ void locate_shard(const SumParams &q, uint32_t i, const uint8_t *&p, uint32_t &len,
+                                             size_t &oi)
+{
+    uint32_t stripe;
+    if (i < q.n_first) {
+        stripe = i / q.per_stripe;
+        p = q.base + (size_t)i * q.stride;
+        oi = (size_t)stripe * q.out_per_stripe + q.out_off + (i - stripe * q.per_stripe);
+    } else {
+        const uint32_t j = i - q.n_first;
+        stripe = j / q.per_stripe2;
+        p = q.base2 + (size_t)j * q.stride;
+        oi = (size_t)stripe * q.out_per_stripe + q.out_off2 + (j - stripe * q.per_stripe2);
+    }
+    len = q.shard_len ? __ldg(q.shard_len + stripe) : q.stride;
+}
 
 __global__ void __launch_bounds__(128) blake2sum_shards_kernel(const __grid_constant__ SumParams q)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n_shards) return;
-    const uint32_t len = q.shard_len ? __ldg(q.shard_len + i / q.per_stripe) : q.stride;
-    const uint8_t *p = q.base + (size_t)i * q.stride;
+    const uint8_t *p;
+    uint32_t len;
+    size_t oi;
+    locate_shard(q, i, p, len, oi);
     Blake2bState S;
     blake2b_init512(S);
     uint64_t m[16];
@@ -846,7 +872,6 @@ __global__ void __launch_bounds__(128) blake2sum_shards_kernel(const __grid_cons
     }
     S.t += rem;
     blake2b_compress(S, m, true);
-    const size_t oi = (size_t)(i / q.per_stripe) * q.out_per_stripe + q.out_off + i % q.per_stripe;
     if (q.sums) {
         uint4 *o = reinterpret_cast<uint4 *>(q.sums + oi * 32);
         o[0] = make_uint4((uint32_t)S.h[0], (uint32_t)(S.h[0] >> 32), (uint32_t)S.h[1], (uint32_t)(S.h[1] >> 32));
@@ -899,8 +924,10 @@ __global__ void __launch_bounds__(kQuadThreads) blake2sum_shards_quad_kernel(con
     const uint32_t i = blockIdx.x * (kQuadThreads / 4) + (tid >> 2);  // shard index
     if (i >= q.n_shards) return;                                      // whole quads leave together
     const uint32_t qmask = 0xFu << (lane & ~3u), qbase = lane & ~3u;
-    const uint32_t len = q.shard_len ? __ldg(q.shard_len + i / q.per_stripe) : q.stride;
-    const uint8_t *p = q.base + (size_t)i * q.stride;
+    const uint8_t *p;
+    uint32_t len;
+    size_t oi;
+    locate_shard(q, i, p, len, oi);
     const uint32_t msg = (uint32_t)__cvta_generic_to_shared(&s_msg[tid >> 2][0]);
 
     // per-round message offsets for this lane: {col x, col y, diag x, diag y} * 8 bytes
@@ -963,7 +990,6 @@ __global__ void __launch_bounds__(kQuadThreads) blake2sum_shards_quad_kernel(con
         if (last) break;
         o += 128;
     }
-    const size_t oi = (size_t)(i / q.per_stripe) * q.out_per_stripe + q.out_off + i % q.per_stripe;
     if (q.sums) *reinterpret_cast<unsigned long long *>(q.sums + oi * 32 + 8 * c) = h0;
     if (q.expect && q.bad) {
         const unsigned long long e = *reinterpret_cast<const unsigned long long *>(q.expect + oi * 32 + 8 * c);

@@ -61,6 +61,7 @@ typedef struct {
     uint64_t reconstruct_calls, reconstruct_batches;
     uint64_t scrub_shards_checked, scrub_corruptions;
     uint64_t resync_queue_length;            /* block.resync_queue_length (all nodes)            */
+    uint64_t encode_call_us, reconstruct_call_us; /* wall time spent inside garage_ec_* batch calls */
 } garage_bm_metrics;
 
 void garage_bm_default_config(garage_bm_config *cfg);
