@@ -22,7 +22,7 @@ SYMBOLS = [
 class Config(C.Structure):
     _fields_ = [("data_shards", C.c_int), ("parity_shards", C.c_int), ("cuda_device", C.c_int),
                 ("n_nodes", C.c_int), ("block_size", C.c_uint32), ("block_ram_buffer_max", C.c_uint64),
-                ("batch_max_blocks", C.c_uint32), ("batch_linger_us", C.c_uint32)]
+                ("batch_max_blocks", C.c_uint32), ("batch_linger_us", C.c_uint32), ("data_dir", C.c_char_p)]
 
 
 class Metrics(C.Structure):
@@ -84,7 +84,7 @@ class BlockManager:
     """Same method names as garage_block::manager::BlockManager where they exist."""
 
     def __init__(self, k=10, m=4, n_nodes=None, cuda_device=0, batch_max_blocks=64, batch_linger_us=200,
-                 block_ram_buffer_max=256 << 20):
+                 block_ram_buffer_max=256 << 20, data_dir=None):
         self._L = load_library()
         cfg = Config()
         self._L.garage_bm_default_config(C.byref(cfg))
@@ -92,6 +92,8 @@ class BlockManager:
         cfg.n_nodes = n_nodes or (k + m)
         cfg.batch_max_blocks, cfg.batch_linger_us = batch_max_blocks, batch_linger_us
         cfg.block_ram_buffer_max = block_ram_buffer_max
+        self._dir = data_dir.encode() if data_dir else None  # keep the bytes alive
+        cfg.data_dir = self._dir
         h = C.c_void_p()
         rc = self._L.garage_bm_create(C.byref(h), C.byref(cfg))
         if rc != OK:

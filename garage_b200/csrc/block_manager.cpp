@@ -17,14 +17,19 @@
 #include <condition_variable>
 #include <cstring>
 #include <deque>
+#include <cstdio>
+#include <filesystem>
 #include <functional>
 #include <future>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
+
+#include <unistd.h>
 
 namespace {
 
@@ -55,13 +60,140 @@ struct StoredShard {
     Hash sum{};  // blake2sum of `bytes` (row f2)
 };
 
+// On-disk shard file (row f3; mirrors the tmp-file -> rename -> .corrupted life cycle of
+// BlockManagerLocked::write_block_inner / move_block_to_corrupted, src/block/manager.rs:720-819,
+// and the directory scheme data_dir/<h[0]>/<h[1]>/<hex(h)> of src/block/layout.rs:286-291):
+//   <data_dir>/node<N>/<hh>/<hh>/<64 hex>.shard        64-byte header + shard bytes
+struct ShardFileHeader {
+    char magic[4];  // "GEC1"
+    uint8_t k, m, index, reserved;
+    uint32_t block_len;
+    uint32_t shard_len;
+    uint8_t sum[32];
+    uint8_t pad[16];
+};
+static_assert(sizeof(ShardFileHeader) == 64, "shard file header is 64 bytes");
+
+std::string hex_of(const uint8_t *p, size_t n)
+{
+    static const char *d = "0123456789abcdef";
+    std::string o;
+    for (size_t i = 0; i < n; i++) {
+        o.push_back(d[p[i] >> 4]);
+        o.push_back(d[p[i] & 15]);
+    }
+    return o;
+}
+
 struct Node {
     std::mutex mu;  // stands in for the 256 hash-sharded mutexes (manager.rs:114,679-689)
     bool up = true;
-    std::unordered_map<Hash, StoredShard, HashHasher> shards;
+    std::string dir;  // empty: in-memory store
+    int k = 0, m = 0;
+    std::unordered_map<Hash, StoredShard, HashHasher> shards;     // in-memory mode
     std::unordered_map<Hash, StoredShard, HashHasher> corrupted;  // the ".corrupted" quarantine
     std::deque<Hash> resync_queue;                                // block_local_resync_queue (resync.rs:90)
     std::unordered_set<Hash, HashHasher> queued;
+
+    std::string path_of(const Hash &h, const char *ext) const
+    {
+        return dir + "/" + hex_of(h.data(), 1) + "/" + hex_of(h.data() + 1, 1) + "/" + hex_of(h.data(), 32) + ext;
+    }
+    // all four are called with `mu` held
+    bool store_put(const Hash &h, StoredShard &&s)
+    {
+        if (dir.empty()) {
+            shards[h] = std::move(s);
+            return true;
+        }
+        std::error_code ec;
+        std::filesystem::create_directories(dir + "/" + hex_of(h.data(), 1) + "/" + hex_of(h.data() + 1, 1), ec);
+        const std::string fin = path_of(h, ".shard"), tmp = fin + ".tmp" + std::to_string((unsigned long)::getpid());
+        ShardFileHeader hd;
+        memset(&hd, 0, sizeof(hd));
+        memcpy(hd.magic, "GEC1", 4);
+        hd.k = (uint8_t)k;
+        hd.m = (uint8_t)m;
+        hd.index = (uint8_t)s.index;
+        hd.block_len = s.block_len;
+        hd.shard_len = (uint32_t)s.bytes.size();
+        memcpy(hd.sum, s.sum.data(), 32);
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f) return false;
+        bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 &&
+                  (s.bytes.empty() || fwrite(s.bytes.data(), s.bytes.size(), 1, f) == 1);
+        ok = (fclose(f) == 0) && ok;
+        if (ok) ok = ::rename(tmp.c_str(), fin.c_str()) == 0;  // atomic publish (manager.rs:790-795)
+        if (!ok) ::remove(tmp.c_str());
+        return ok;
+    }
+    bool store_get(const Hash &h, StoredShard &out) const
+    {
+        if (dir.empty()) {
+            auto it = shards.find(h);
+            if (it == shards.end()) return false;
+            out = it->second;
+            return true;
+        }
+        FILE *f = fopen(path_of(h, ".shard").c_str(), "rb");  // find_block (manager.rs:627-662)
+        if (!f) return false;
+        ShardFileHeader hd;
+        bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "GEC1", 4) == 0;
+        if (ok) {
+            out.index = hd.index;
+            out.block_len = hd.block_len;
+            memcpy(out.sum.data(), hd.sum, 32);
+            out.bytes.resize(hd.shard_len);
+            ok = hd.shard_len == 0 || fread(out.bytes.data(), hd.shard_len, 1, f) == 1;
+        }
+        fclose(f);
+        return ok;
+    }
+    bool store_has(const Hash &h) const
+    {
+        if (dir.empty()) return shards.count(h) != 0;
+        std::error_code ec;
+        return std::filesystem::exists(path_of(h, ".shard"), ec);
+    }
+    bool store_erase(const Hash &h)
+    {
+        if (dir.empty()) return shards.erase(h) != 0;
+        return ::remove(path_of(h, ".shard").c_str()) == 0;
+    }
+    void store_quarantine(const Hash &h)  // move_block_to_corrupted (manager.rs:807-819)
+    {
+        if (dir.empty()) {
+            auto it = shards.find(h);
+            if (it != shards.end()) {
+                corrupted[h] = std::move(it->second);
+                shards.erase(it);
+            }
+            return;
+        }
+        ::rename(path_of(h, ".shard").c_str(), path_of(h, ".corrupted").c_str());
+    }
+    void store_list(std::vector<Hash> &out) const  // BlockStoreIterator (repair.rs:634-764)
+    {
+        if (dir.empty()) {
+            for (auto &kv : shards) out.push_back(kv.first);
+            return;
+        }
+        std::error_code ec;
+        for (auto it = std::filesystem::recursive_directory_iterator(dir, ec);
+             !ec && it != std::filesystem::recursive_directory_iterator(); it.increment(ec)) {
+            const std::string name = it->path().filename().string();
+            if (name.size() != 64 + 6 || name.compare(64, 6, ".shard") != 0) continue;
+            Hash h;
+            bool ok = true;
+            for (int i = 0; i < 32 && ok; i++) {
+                auto v = [&](char c) { return c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : -1); };
+                const int hi = v(name[2 * i]), lo = v(name[2 * i + 1]);
+                ok = hi >= 0 && lo >= 0;
+                h[i] = (uint8_t)((hi << 4) | lo);
+            }
+            if (ok) out.push_back(h);
+        }
+    }
 };
 
 // ---------------------------------------------------------------- counting semaphore (bytes)
@@ -302,7 +434,7 @@ struct garage_bm {
         s.sum = sum;
         Node &nd = *nodes[node];
         std::lock_guard<std::mutex> lk(nd.mu);
-        nd.shards[h] = std::move(s);
+        nd.store_put(h, std::move(s));
         bytes_written += n;
     }
 
@@ -314,9 +446,7 @@ struct garage_bm {
         {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return false;
-            auto it = nd.shards.find(h);
-            if (it == nd.shards.end()) return false;
-            out = it->second;
+            if (!nd.store_get(h, out)) return false;
         }
         bytes_read += out.bytes.size();
         Hash got;
@@ -325,11 +455,7 @@ struct garage_bm {
         corruption_counter++;
         {
             std::lock_guard<std::mutex> lk(nd.mu);
-            auto it = nd.shards.find(h);
-            if (it != nd.shards.end()) {
-                nd.corrupted[h] = std::move(it->second);
-                nd.shards.erase(it);
-            }
+            nd.store_quarantine(h);
         }
         put_to_resync(node, h);
         return false;
@@ -545,7 +671,7 @@ struct garage_bm {
             Node &nd = *nodes[node];
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return GARAGE_BM_E_MESSAGE;
-            if (nd.shards.count(h)) return GARAGE_BM_OK;  // exists
+            if (nd.store_has(h)) return GARAGE_BM_OK;  // exists
         }
         std::vector<StoredShard> got;
         std::vector<uint8_t> have;
@@ -628,7 +754,7 @@ struct garage_bm {
             bool has;
             {
                 std::lock_guard<std::mutex> lk(nodes[node]->mu);
-                has = nodes[node]->shards.count(h) != 0;
+                has = nodes[node]->store_has(h);
             }
             if (!has) {
                 put_to_resync(node, h);
@@ -648,7 +774,7 @@ struct garage_bm {
         {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return GARAGE_BM_E_MESSAGE;
-            for (auto &kv : nd.shards) hashes.push_back(kv.first);
+            nd.store_list(hashes);
         }
         uint64_t nchecked = 0, nbad = 0;
         const size_t chunk = std::max<size_t>(1, (size_t)cfg.batch_max_blocks * tot);
@@ -660,9 +786,7 @@ struct garage_bm {
             {
                 std::lock_guard<std::mutex> lk(nd.mu);
                 for (size_t i = 0; i < n; i++) {
-                    auto it = nd.shards.find(hashes[c0 + i]);
-                    if (it == nd.shards.end()) continue;
-                    snap[i] = it->second;
+                    if (!nd.store_get(hashes[c0 + i], snap[i])) continue;
                     ok[i] = 1;
                     max_len = std::max<uint32_t>(max_len, (uint32_t)snap[i].bytes.size());
                 }
@@ -692,11 +816,7 @@ struct garage_bm {
                 corruption_counter++;
                 {
                     std::lock_guard<std::mutex> lk(nd.mu);
-                    auto it = nd.shards.find(hashes[c0 + i]);
-                    if (it != nd.shards.end()) {
-                        nd.corrupted[hashes[c0 + i]] = std::move(it->second);
-                        nd.shards.erase(it);
-                    }
+                    nd.store_quarantine(hashes[c0 + i]);
                 }
                 put_to_resync(node, hashes[c0 + i]);
             }
@@ -723,6 +843,7 @@ void garage_bm_default_config(garage_bm_config *c)
     c->block_ram_buffer_max = 256ull << 20;  // util/config.rs:276-278
     c->batch_max_blocks = 64;
     c->batch_linger_us = 200;
+    c->data_dir = nullptr;
 }
 
 int garage_bm_create(garage_bm **out, const garage_bm_config *cfg)
@@ -738,7 +859,24 @@ int garage_bm_create(garage_bm **out, const garage_bm_config *cfg)
     bm->tot = k + m;
     int rc = garage_ec_create(&bm->ec, cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
     if (rc != GARAGE_EC_OK) return rc;  // no GPU => no block manager: there is no CPU fallback
-    for (int i = 0; i < cfg->n_nodes; i++) bm->nodes.emplace_back(new Node());
+    for (int i = 0; i < cfg->n_nodes; i++) {
+        bm->nodes.emplace_back(new Node());
+        Node &nd = *bm->nodes.back();
+        nd.k = k;
+        nd.m = m;
+        if (cfg->data_dir && cfg->data_dir[0]) {
+            nd.dir = std::string(cfg->data_dir) + "/node" + std::to_string(i);
+            std::error_code ec;
+            std::filesystem::create_directories(nd.dir, ec);
+            // restart: what is on disk is what exists (the block_ref table would say the same)
+            std::vector<Hash> have;
+            nd.store_list(have);
+            for (const Hash &h : have) {
+                StoredShard sh;
+                if (nd.store_get(h, sh)) bm->refs[h] = sh.block_len;
+            }
+        }
+    }
     bm->ram.reset(new ByteSemaphore(cfg->block_ram_buffer_max ? cfg->block_ram_buffer_max : (256ull << 20)));
     bm->scrub_buf.ctx = bm->ec;
     for (int w = 0; w < garage_bm::kWorkers; w++) {
@@ -843,9 +981,10 @@ int garage_bm_corrupt_shard(garage_bm *bm, int node, const uint8_t hash[32], siz
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
     Node &nd = *bm->nodes[node];
     std::lock_guard<std::mutex> lk(nd.mu);
-    auto it = nd.shards.find(to_hash(hash));
-    if (it == nd.shards.end() || it->second.bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
-    it->second.bytes[byte_off % it->second.bytes.size()] ^= 0x01;
+    StoredShard sh;
+    if (!nd.store_get(to_hash(hash), sh) || sh.bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
+    sh.bytes[byte_off % sh.bytes.size()] ^= 0x01;  // the stored sum is left alone: that is the corruption
+    nd.store_put(to_hash(hash), std::move(sh));
     return GARAGE_BM_OK;
 }
 
@@ -854,7 +993,7 @@ int garage_bm_drop_shard(garage_bm *bm, int node, const uint8_t hash[32])
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
     Node &nd = *bm->nodes[node];
     std::lock_guard<std::mutex> lk(nd.mu);
-    if (nd.shards.erase(to_hash(hash))) {
+    if (nd.store_erase(to_hash(hash))) {
         bm->delete_counter++;
         return GARAGE_BM_OK;
     }
@@ -866,8 +1005,8 @@ int garage_bm_node_shard_index(garage_bm *bm, int node, const uint8_t hash[32])
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return -1;
     Node &nd = *bm->nodes[node];
     std::lock_guard<std::mutex> lk(nd.mu);
-    auto it = nd.shards.find(to_hash(hash));
-    return it == nd.shards.end() ? -1 : it->second.index;
+    StoredShard sh;
+    return nd.store_get(to_hash(hash), sh) ? sh.index : -1;
 }
 
 int garage_bm_storage_nodes_of(garage_bm *bm, const uint8_t hash[32], int *nodes_out)

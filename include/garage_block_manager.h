@@ -50,6 +50,9 @@ typedef struct {
     uint64_t block_ram_buffer_max;  /* util/config.rs:276-278, default 256 MiB        */
     uint32_t batch_max_blocks;      /* f1: max blocks per GPU batch                   */
     uint32_t batch_linger_us;       /* f1: how long the first block of a batch waits  */
+    const char *data_dir;           /* NULL/"": shards in memory; else <data_dir>/node<N>/<hh>/<hh>/<hash>.shard
+                                       (64-byte header {GEC1,k,m,index,block_len,shard_len,blake2sum} + bytes;
+                                       tmp-file -> rename, *.corrupted quarantine: manager.rs:720-819)  */
 } garage_bm_config;
 
 typedef struct {

@@ -205,3 +205,37 @@ def test_concurrent_puts_are_batched():
             for b in blocks[t]:
                 rc, got = bm.rpc_get_block(BM.blake2sum(b))
                 assert rc == BM.OK and np.array_equal(got, b)
+
+
+@pytest.mark.gpu
+def test_file_backed_store_survives_restart(tmp_path):
+    """row f3: shards on disk as <data_dir>/node<N>/<hh>/<hh>/<hash>.shard (header + bytes), written
+    tmp -> rename; a new BlockManager on the same directory serves the same blocks; a corrupt file
+    is renamed *.corrupted and rebuilt by resync."""
+    k, m = 4, 2
+    blocks = [O.fill_random(n, 300 + i) for i, n in enumerate([1 << 20, 3073, 500000])]
+    d = str(tmp_path / "data")
+    with BM.BlockManager(k, m, data_dir=d) as bm:
+        hashes = put_all(bm, blocks)
+    files = sorted(p for p in (tmp_path / "data").rglob("*.shard"))
+    assert len(files) == len(blocks) * (k + m)
+    f0 = files[0]
+    assert f0.parent.name == f0.name[2:4] and f0.parent.parent.name == f0.name[0:2]  # layout.rs:286-291
+    raw = f0.read_bytes()
+    assert raw[:4] == b"GEC1" and raw[4] == k and raw[5] == m
+    shard_len = int.from_bytes(raw[12:16], "little")
+    assert len(raw) == 64 + shard_len
+    assert raw[16:48] == hashlib.blake2b(raw[64:]).digest()[:32]  # per-shard blake2sum in the header
+    assert not list((tmp_path / "data").rglob("*.tmp*"))
+    with BM.BlockManager(k, m, data_dir=d) as bm:  # "restart"
+        for h, b in zip(hashes, blocks):
+            rc, got = bm.rpc_get_block(h)
+            assert rc == BM.OK and np.array_equal(got, b)
+        who = bm.storage_nodes_of(hashes[0])
+        assert bm.corrupt_shard(who[1], hashes[0], 77) == BM.OK
+        rc, got = bm.rpc_get_block(hashes[0])
+        assert rc == BM.OK and np.array_equal(got, blocks[0])
+        assert len(list((tmp_path / "data").rglob("*.corrupted"))) == 1
+        assert bm.resync_all(who[1]) == (0, 1)
+        rc, checked, corrupt = bm.scrub(who[1])
+        assert (rc, corrupt) == (BM.OK, 0) and checked >= 1
