@@ -145,7 +145,7 @@ cudaError_t launch_apply_t(const garage_ec_ctx *ctx, const ApplyParams &p, cudaS
         if (e != cudaSuccess) return e;
         configured_for_device.store(ctx->device, std::memory_order_release);
     }
-    kern<<<ctx->sm_count, NT, ctx->smem_bytes, st>>>(p);
+    kern<<<ctx->sm_count * GEC_MIN_BLOCKS, NT, ctx->smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -71,8 +71,14 @@ constexpr uint32_t kGroupBytes = 32768;  // one table group: 256 rows x 32 banks
 // tables per 32 KB group for k sources: smallest G (least padding) whose groups need <= 192 KB,
 // so that >= 32 KB of the SM's 228 KB stay L1 (with 224 KB of tables the global loads starve:
 // k = 7 measured 0.65 of peak against 0.92 for k = 6)
+#ifndef GEC_MIN_BLOCKS
+#define GEC_MIN_BLOCKS 1  // CTAs per SM the streaming kernel is sized for (tuning experiments only)
+#endif
 __host__ __device__ constexpr int log2_group_for_k(int k)
 {
+#ifdef GEC_FORCE_LG
+    return GEC_FORCE_LG;
+#endif
     return k <= 6 ? 0 : (k <= 12 ? 1 : (k <= 24 ? 2 : 3));
 }
 __host__ __device__ constexpr int slots_for_k(int k)
@@ -410,7 +416,7 @@ __device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t 
 
 // ------------------------------------------------------------------ the streaming kernel
 template <int K, int MODE, int NT, bool PIPE>
-__global__ void __launch_bounds__(NT, 1) rs_apply_kernel(const __grid_constant__ ApplyParams p)
+__global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __grid_constant__ ApplyParams p)
 {
     constexpr int kThreads = NT;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
