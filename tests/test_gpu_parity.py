@@ -411,3 +411,34 @@ def test_thread_safety_device_calls(torch):
         [t.start() for t in th]
         [t.join() for t in th]
         assert not errs
+
+
+def test_host_mode_concurrent_callers_one_context(torch):
+    """HOST-mode calls from several OS threads on ONE context (they share the staging lanes and
+    are serialised inside the library) must each get the right bytes."""
+    k, m, stride, n = 6, 3, 8192, 40
+    P = O.build_matrix(k, m, 0)
+    datas = [O.fill_random(n * k * stride, 900 + i) for i in range(4)]
+    wants = [O.encode(k, m, P, d, stride, n, simd=True) for d in datas]
+    with G.GarageEc(0, k, m) as ec:
+        errs = []
+
+        def work(i):
+            try:
+                for _ in range(3):
+                    out = np.zeros(n * m * stride, dtype=np.uint8)
+                    ec.encode(datas[i], out, stride, n)
+                    if not np.array_equal(out, wants[i]):
+                        errs.append(i)
+                    sh = np.concatenate([datas[i].reshape(n, k, stride), wants[i].reshape(n, m, stride)], axis=1)
+                    mm = np.ones(n, dtype=np.uint32)
+                    ec.verify(np.ascontiguousarray(sh).reshape(-1), mm, stride, n)
+                    if mm.any():
+                        errs.append(("verify", i))
+            except Exception as ex:  # noqa: BLE001
+                errs.append(repr(ex))
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs
