@@ -532,10 +532,12 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
         // Two plan slots: while the CTA streams stripe `cur`, warp 0 claims the next stripe and
         // stages its plan; at the stripe boundary the first column loads of the new stripe are
         // issued BEFORE its tables are rebuilt, so HBM latency hides behind the rebuild.
+        // Stripes are claimed one staging ahead: the atomic issued now is consumed by the NEXT call,
+        // so its round trip never sits between the CTA and the barrier that waits for the plan.
+        uint32_t claimed = 0;                  // meaningful in lane 0 of warp 0
         auto stage_plan = [&](PlanSlot &ps) {  // executed by warp 0 only
-            uint32_t s = 0;
-            if (lane == 0) s = atomicAdd(p.counter, 1u);
-            s = __shfl_sync(0xffffffffu, s, 0);
+            const uint32_t s = __shfl_sync(0xffffffffu, claimed, 0);
+            if (lane == 0) claimed = atomicAdd(p.counter, 1u);
             int rows = 0;
             if (s < p.n) {
                 const StripePlan *pl = p.plan + s;
@@ -556,7 +558,10 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
                 ps.rows = rows;
             }
         };
-        if (warp == 0) stage_plan(L.slot[0]);
+        if (warp == 0) {
+            if (lane == 0) claimed = atomicAdd(p.counter, 1u);
+            stage_plan(L.slot[0]);
+        }
         __syncthreads();
         unsigned long long built_present = ~0ull, built_out = ~0ull;
         bool have_tables = false;
