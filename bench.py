@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--m", type=int, default=4)
     ap.add_argument("--blocks", type=int, default=4096, help="1 MiB blocks per GPU per pass")
     ap.add_argument("--e2e-blocks", type=int, default=0, help="blocks per e2e step (0 = --blocks)")
-    ap.add_argument("--cpu-blocks", type=int, default=256, help="blocks per CPU-arm step")
+    ap.add_argument("--cpu-blocks", type=int, default=0,
+                    help="blocks per CPU-arm step (0 = auto: max(512, 16 per host thread), capped at 4096 -- "
+                         "with fewer blocks per thread the pthread fan-out dominates and the CPU looks slower than it is)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scrub/repair sweep extra")
@@ -147,6 +149,8 @@ def cpu_arm(k, m, nblocks, steps, warmup, budget_s=None):
     stride = (L + 127) // 128 * 128
     tot = k + m
     threads = O.lib().rs_simd_max_threads()
+    if nblocks <= 0:
+        nblocks = min(4096, max(512, 16 * threads))
     P = O.build_matrix(k, m, 0)
     shards = np.zeros((nblocks, tot, stride), dtype=np.uint8)
     for s in range(nblocks):
