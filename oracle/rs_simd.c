@@ -354,6 +354,34 @@ static void *worker(void *arg)
 	return NULL;
 }
 
+/* Persistent worker pool: creating 128 pthreads per call costs milliseconds, which is a large part
+ * of a call on a big host and would understate the CPU arm.  Workers sleep on a condition variable;
+ * a call publishes `threads` job slots, workers (and the caller) grab slots until none are left. */
+static struct {
+	pthread_mutex_t mu;
+	pthread_cond_t work, done;
+	int nthreads;          /* workers created so far */
+	struct job *jobs;      /* current batch */
+	int njobs, next, remaining;
+	unsigned long epoch;
+} g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, NULL, 0, 0, 0, 0 };
+static pthread_mutex_t g_call_mu = PTHREAD_MUTEX_INITIALIZER; /* one batch at a time */
+
+static void *pool_main(void *arg)
+{
+	(void)arg;
+	pthread_mutex_lock(&g_pool.mu);
+	for (;;) {
+		while (g_pool.next >= g_pool.njobs) pthread_cond_wait(&g_pool.work, &g_pool.mu);
+		struct job *jb = &g_pool.jobs[g_pool.next++];
+		pthread_mutex_unlock(&g_pool.mu);
+		worker(jb);
+		pthread_mutex_lock(&g_pool.mu);
+		if (--g_pool.remaining == 0) pthread_cond_broadcast(&g_pool.done);
+	}
+	return NULL;
+}
+
 static size_t run_jobs(struct job *proto, size_t n, int threads)
 {
 	if (threads < 1) threads = rs_simd_max_threads();
@@ -361,20 +389,48 @@ static size_t run_jobs(struct job *proto, size_t n, int threads)
 	rs_oracle_gf_mul(1, 1); /* make sure the oracle tables are built before fan-out */
 	(void)isa();
 	struct job *jobs = calloc((size_t)threads, sizeof(*jobs));
-	pthread_t *th = calloc((size_t)threads, sizeof(*th));
 	size_t bad = 0;
 	for (int t = 0; t < threads; t++) {
 		jobs[t] = *proto;
 		jobs[t].s0 = n * (size_t)t / (size_t)threads;
 		jobs[t].s1 = n * (size_t)(t + 1) / (size_t)threads;
 		jobs[t].bad = 0;
-		if (t + 1 < threads) pthread_create(&th[t], NULL, worker, &jobs[t]);
 	}
-	worker(&jobs[threads - 1]);
-	for (int t = 0; t + 1 < threads; t++) pthread_join(th[t], NULL);
+	pthread_mutex_lock(&g_call_mu);
+	pthread_mutex_lock(&g_pool.mu);
+	while (g_pool.nthreads < threads - 1) { /* the caller is the last worker */
+		pthread_t th;
+		pthread_attr_t at;
+		pthread_attr_init(&at);
+		pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+		if (pthread_create(&th, &at, pool_main, NULL) != 0) {
+			pthread_attr_destroy(&at);
+			break;
+		}
+		pthread_attr_destroy(&at);
+		g_pool.nthreads++;
+	}
+	g_pool.jobs = jobs;
+	g_pool.njobs = threads;
+	g_pool.next = 0;
+	g_pool.remaining = threads;
+	pthread_cond_broadcast(&g_pool.work);
+	/* the caller works too */
+	while (g_pool.next < g_pool.njobs) {
+		struct job *jb = &g_pool.jobs[g_pool.next++];
+		pthread_mutex_unlock(&g_pool.mu);
+		worker(jb);
+		pthread_mutex_lock(&g_pool.mu);
+		if (--g_pool.remaining == 0) pthread_cond_broadcast(&g_pool.done);
+	}
+	while (g_pool.remaining > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+	g_pool.njobs = 0;
+	g_pool.next = 0;
+	g_pool.jobs = NULL;
+	pthread_mutex_unlock(&g_pool.mu);
+	pthread_mutex_unlock(&g_call_mu);
 	for (int t = 0; t < threads; t++) bad += jobs[t].bad;
 	free(jobs);
-	free(th);
 	return bad;
 }
 
