@@ -74,12 +74,14 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """samples SM clock + throttle reasons on one GPU while the timed region runs"""
+    """SM clock + throttle reasons of one GPU, sampled by the MAIN thread after all timed steps have
+    been enqueued and until their end event completes: every sample is taken under load inside the
+    timed region, and no NVML call competes with a kernel launch for the driver (a background
+    sampler thread did: one run showed 0.7 ms of launch gaps per 2 ms step)."""
 
     def __init__(self, index):
         self.index, self.samples, self.reasons = index, [], set()
-        self.max_mhz, self.err, self._stop = None, None, threading.Event()
-        self._t = None
+        self.max_mhz, self.err = None, None
         try:
             import pynvml
 
@@ -90,8 +92,10 @@ class ClockSampler:
         except Exception as e:  # noqa: BLE001
             self.nv, self.err = None, repr(e)
 
-    def _run(self):
+    def sample(self):
         nv = self.nv
+        if not nv:
+            return
         names = {
             "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
             "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
@@ -99,31 +103,23 @@ class ClockSampler:
             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
             "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
         }
-        while not self._stop.is_set():
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:  # older binding name
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for n, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(n)
-            except Exception as e:  # noqa: BLE001
-                self.err = repr(e)
-                break
-            self._stop.wait(0.01)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:  # older binding name
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for n, bit in names.items():
+                if r & bit:
+                    self.reasons.add(n)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
-    def __enter__(self):
-        if self.nv:
-            self._t = threading.Thread(target=self._run, daemon=True)
-            self._t.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        if self._t:
-            self._t.join()
+    def sample_until(self, end_event, max_samples=200):
+        """poll while the GPU is still inside the timed region"""
+        while not end_event.query() and len(self.samples) < max_samples:
+            self.sample()
+            time.sleep(0.004)
 
     def summary(self):
         if not self.samples:
@@ -164,7 +160,11 @@ def cpu_arm(k, m, nblocks, steps, warmup, budget_s=None):
         present[s, rng.choice(tot, m, replace=False)] = 0
     par = O.encode(k, m, P, data, stride, nblocks, lens, simd=True)
     shards[:, k:] = par.reshape(nblocks, m, stride)
-    flat = shards.reshape(-1)
+    # NUMA: place every stripe on the memory node of the worker thread that processes it
+    data = O.numa_local_copy(data, k * stride, nblocks, threads)
+    par = O.numa_local_copy(par, m * stride, nblocks, threads)
+    flat = O.numa_local_copy(shards.reshape(-1), tot * stride, nblocks, threads)
+    del shards
     t_enc = t_dec = 0.0
     done = 0
     t_start = time.perf_counter()
@@ -287,13 +287,14 @@ def run_ours(args, rank, world, local_rank):
     enc.timing_read(), dec.timing_read()
     l0 = enc.launch_count() + dec.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            step()
-        ev1.record()
-        barrier()
+    clk = ClockSampler(local_rank)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    clk.sample_until(ev1)  # the host is ahead of the GPU: these samples fall inside the timed region
+    barrier()
     ms = ev0.elapsed_time(ev1)
     launches = enc.launch_count() + dec.launch_count() - l0
     enc_ms, enc_n = enc.timing_read()

@@ -238,7 +238,10 @@ void rs_simd_rows(int k, int rows, const uint8_t *C, const uint8_t *const *in, u
 
 /* ------------------------------------------------------------------ threaded batch drivers */
 struct job {
-	int op; /* 0 encode, 1 reconstruct, 2 verify */
+	int op; /* 0 encode, 1 reconstruct, 2 verify, 3 copy (first touch) */
+	const uint8_t *cp_src;
+	uint8_t *cp_dst;
+	size_t cp_bytes; /* per stripe */
 	int k, m;
 	const uint8_t *P;
 	const uint8_t *data;
@@ -280,6 +283,11 @@ static void encode_one(int k, int rows, const uint8_t *C, const uint8_t *const *
 static void *worker(void *arg)
 {
 	struct job *jb = (struct job *)arg;
+	if (jb->op == 3) {
+		for (size_t s = jb->s0; s < jb->s1; s++)
+			memcpy(jb->cp_dst + s * jb->cp_bytes, jb->cp_src + s * jb->cp_bytes, jb->cp_bytes);
+		return NULL;
+	}
 	const int k = jb->k, m = jb->m, tot = k + m;
 	const uint8_t *in[256];
 	uint8_t *out[256];
@@ -457,5 +465,15 @@ void rs_simd_verify(int k, int m, const uint8_t *P, const uint8_t *shards, uint3
 {
 	struct job jb = { .op = 2, .k = k, .m = m, .P = P, .shards = (uint8_t *)shards,
 			  .mismatch = mismatch, .shard_len = shard_len, .stride = stride };
+	run_jobs(&jb, n, threads);
+}
+
+/* NUMA first touch: copies n stripes of `bytes_per_stripe` with the same stripe->thread partition
+ * the drivers above use, so that a fresh (untouched) destination ends up on the memory node of the
+ * thread that will process it.  Without it a 128-thread host streams everything from the node of
+ * the thread that generated the data (measured: 12 GiB/s instead of > 40). */
+void rs_simd_parallel_copy(uint8_t *dst, const uint8_t *src, size_t bytes_per_stripe, size_t n, int threads)
+{
+	struct job jb = { .op = 3, .cp_src = src, .cp_dst = dst, .cp_bytes = bytes_per_stripe };
 	run_jobs(&jb, n, threads);
 }

@@ -68,6 +68,8 @@ def lib():
                                           C.c_void_p] + geo + [C.c_int]
         L.rs_simd_verify.restype = None
         L.rs_simd_verify.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + geo + [C.c_int]
+        L.rs_simd_parallel_copy.restype = None
+        L.rs_simd_parallel_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
         L.rs_simd_isa.restype = C.c_char_p
         L.rs_simd_max_threads.restype = C.c_int
         L.rs_simd_force_isa.restype = C.c_int
@@ -132,6 +134,13 @@ def verify(k, m, P, shards, stride, n, shard_len=None, simd=False, threads=0):
     else:
         lib().rs_oracle_verify(k, m, _p(P), _p(shards), _p(mm), _p(sl), stride, n)
     return mm
+
+
+def numa_local_copy(a, bytes_per_stripe, n, threads=0):
+    """copy of `a` whose pages are first touched by the worker threads that will process them"""
+    out = np.empty_like(a)
+    lib().rs_simd_parallel_copy(_p(out), _p(a), bytes_per_stripe, n, threads)
+    return out
 
 
 def fill_random(n, seed, offset=0):
