@@ -442,3 +442,43 @@ def test_host_mode_concurrent_callers_one_context(torch):
         [t.start() for t in th]
         [t.join() for t in th]
         assert not errs
+
+
+def test_device_calls_are_cuda_graph_capturable(torch):
+    """DEVICE-mode encode / reconstruct / verify enqueue only kernels and stream-ordered
+    allocations, so a caller can capture them once and replay (no host work per batch)."""
+    k, m, stride, n = 10, 4, 4096, 64
+    tot = k + m
+    P, orig = make_stripes(k, m, 0, n, stride, None, 77)
+    present = np.ones((n, tot), dtype=np.uint8)
+    rng = np.random.default_rng(1)
+    for s in range(n):
+        present[s, rng.choice(tot, m, replace=False)] = 0
+    with G.GarageEc(0, k, m) as ec:
+        data = dev(torch, orig[:, :k].reshape(-1))
+        par = torch.zeros(n * m * stride, dtype=torch.uint8, device="cuda")
+        sh = dev(torch, orig.reshape(-1))
+        pd = dev(torch, present)
+        st = torch.ones(n, dtype=torch.int32, device="cuda")
+        mm = torch.ones(n, dtype=torch.int32, device="cuda")
+
+        def step():
+            ec.encode(data, par, stride, n)
+            ec.reconstruct(sh, pd, stride, n, status=st)
+            ec.verify(sh, mm, stride, n)
+
+        step()  # warm-up outside capture (function attributes, allocator pool)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        for trial in range(3):
+            par.zero_()
+            sh.view(n, tot, stride)[~pd.bool()] = trial  # wipe the erased shards
+            st.fill_(9)
+            mm.fill_(9)
+            g.replay()
+            torch.cuda.synchronize()
+            assert np.array_equal(host(par).reshape(n, m, stride), orig[:, k:])
+            assert np.array_equal(host(sh).reshape(n, tot, stride), orig)
+            assert not host(st).any() and not host(mm).any()
