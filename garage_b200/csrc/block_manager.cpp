@@ -538,7 +538,7 @@ struct garage_bm {
 
     // gather the valid shards of `h` from every up node except `skip_node`
     int gather(const Hash &h, int skip_node, std::vector<StoredShard> &got, std::vector<uint8_t> &have,
-               uint32_t &block_len, bool data_first_only)
+               uint32_t &block_len)
     {
         int who[64];
         storage_nodes_of(h, who);
@@ -558,7 +558,6 @@ struct garage_bm {
         // data shards first (a complete set needs no GPU), then only as many parity shards as
         // it takes to reach k -- the reference likewise stops at the first good copy
         // (manager.rs:292-334); RpcHelper::try_call_many with quorum k is the real-cluster form
-        (void)data_first_only;
         for (int i = 0; i < k; i++) try_shard(i);
         for (int i = k; i < tot && count < k; i++) try_shard(i);
         return count;
@@ -625,7 +624,7 @@ struct garage_bm {
         std::vector<StoredShard> got;
         std::vector<uint8_t> have;
         uint32_t block_len = 0;
-        const int count = gather(h, -1, got, have, block_len, true);
+        const int count = gather(h, -1, got, have, block_len);
         if (count < k) return GARAGE_BM_E_MISSING_BLOCK;  // manager.rs:336-338
         const size_t L = garage_ec_shard_len(block_len, k);
         bool all_data = true;
@@ -676,7 +675,7 @@ struct garage_bm {
         std::vector<StoredShard> got;
         std::vector<uint8_t> have;
         uint32_t block_len = 0;
-        const int count = gather(h, node, got, have, block_len, false);
+        const int count = gather(h, node, got, have, block_len);
         if (count < k) {
             resync_error_counter++;
             return GARAGE_BM_E_MISSING_BLOCK;  // resync.rs:488-494

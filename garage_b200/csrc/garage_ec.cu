@@ -878,7 +878,7 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
     if (n_stripes == 0) return GARAGE_EC_OK;
     if (!shards || !expect_sums || !bad_out) return GARAGE_EC_E_INVALID;
     if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
-    const size_t k = ctx->k, tot = ctx->k + ctx->m;
+    const size_t tot = ctx->k + ctx->m;
     if (n_stripes * tot > 0xffffffffull) return GARAGE_EC_E_INVALID;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (mem_kind == GARAGE_EC_MEM_DEVICE) {
@@ -970,7 +970,6 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
         if (rc) return rc;
     }
     for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
-    (void)k;
     for (size_t s = 0; s < n_stripes; s++)
         if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
     return GARAGE_EC_OK;
