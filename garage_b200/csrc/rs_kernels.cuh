@@ -377,7 +377,7 @@ __device__ __forceinline__ void column_compute(uint4 (&d)[slots_for_k(K)], uint3
     rows_from_acc(acc, r);
 }
 
-// generic k (runtime): one group of G slots at a time, no cross-column prefetch
+// generic k (runtime, k > 16): batches of 8 slots, the next batch prefetched while one is looked up
 template <bool kPlan>
 __device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t stride, uint32_t k_rt,
                                                     const uint32_t *src_off, uint32_t tab_base,
@@ -391,10 +391,10 @@ __device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t 
     uint32_t acc[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i] = 0;
-    for (uint32_t u0 = 0; u0 < slots; u0 += 4) {
-        uint4 d[4];
+    constexpr int W = 8;  // slots per batch; the next batch is in flight while this one is looked up
+    auto load_batch = [&](uint32_t u0, uint4 (&d)[W]) {
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
+        for (int v = 0; v < W; v++) {
             const uint32_t j = (u0 + v) ^ q;
             d[v] = make_uint4(0, 0, 0, 0);
             if (u0 + v < slots && j < k_rt) {
@@ -402,8 +402,16 @@ __device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t 
                 if (tail_bytes) d[v] = mask_tail(d[v], tail_bytes);
             }
         }
+    };
+    uint4 dn[W];
+    load_batch(0, dn);
+    for (uint32_t u0 = 0; u0 < slots; u0 += W) {
+        uint4 d[W];
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
+        for (int v = 0; v < W; v++) d[v] = dn[v];
+        if (u0 + W < slots) load_batch(u0 + W, dn);
+#pragma unroll
+        for (int v = 0; v < W; v++) {
             const uint32_t u = u0 + v;
             if (u < slots) {
                 const uint32_t base = tab_base + ((lane ^ ((u & (G - 1)) * R)) << 2) + (u >> lg) * kGroupBytes;
