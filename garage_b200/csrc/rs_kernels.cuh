@@ -196,6 +196,8 @@ struct PlanSlot {
     unsigned long long key_present, key_out;
     uint32_t sid;   // stripe index (>= n: no more work)
     int32_t rows;   // rows to produce in this pass (<= 0: nothing to do)
+    uint32_t chunk_next;  // next unclaimed 32-column chunk of this stripe (warps claim them dynamically)
+    uint32_t pad;
     uint32_t src_off[kMaxK];           // byte offset of source j inside the stripe
     uint32_t dst_off[kRowsPerPass];    // byte offset of output row i inside the stripe
     uint8_t coef[kRowsPerPass * kMaxK];  // coef[i*kMaxK + j]
@@ -564,6 +566,7 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
             if (lane == 0) {
                 ps.sid = s;
                 ps.rows = rows;
+                ps.chunk_next = kThreads / 32;  // chunk w < #warps belongs to warp w, the rest are claimed
             }
         };
         if (warp == 0) {
@@ -601,16 +604,29 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
             __syncthreads();  // tables of `s` complete, next plan staged
             if (rows > 0) {
                 if (K > 0 && PIPE) {
-                    while (col < nvec) {
+                    // 32-column chunks: chunk `warp` is this warp's first one, the rest are claimed
+                    // from a shared counter one iteration ahead, so every warp reaches the barrier
+                    // within one chunk of the others (a static col = tid + i*NT split lets the slow
+                    // warps' lag accumulate over the ~13 iterations of a stripe)
+                    // claims run one iteration ahead of their use, so the shared-memory atomic
+                    // never delays the prefetch loads.  Measured (profiles/r01_summary.md): RS(10,4)
+                    // with 4 erasures 0.905 -> 0.926, RS(6,3) 0.867 -> 0.905, RS(4,2) 0.949 -> 0.976;
+                    // a single erasure per stripe is slower than with the static split (0.91 -> 0.86).
+                    uint32_t chunk = warp, nxt = 0, nxt2 = 0;
+                    if (lane == 0) nxt = atomicAdd(&L.slot[cs].chunk_next, 1u);
+                    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+                    while (chunk * 32 < nvec) {
                         uint4 d[SD];
 #pragma unroll
                         for (int u = 0; u < SD; u++) d[u] = dn[u];
-                        const uint32_t cur = col;
-                        col += kThreads;
-                        if (col < nvec) {
-                            column_load<KD, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, q, dn);
+                        const uint32_t cur = chunk * 32 + lane;
+                        if (lane == 0) nxt2 = atomicAdd(&L.slot[cs].chunk_next, 1u);  // consumed next iteration
+                        if (nxt * 32 < nvec) {
+                            const uint32_t ncol = nxt * 32 + lane;
+                            if (ncol < nvec)
+                                column_load<KD, true>(sbase + (size_t)ncol * 16, p.stride, ps.src_off, q, dn);
                         } else {
-                            // last column of this thread in this stripe: start on the next stripe
+                            // no chunk left in this stripe for this warp: start on the next stripe
                             // (its plan was staged before the barrier above) so HBM never drains
                             const PlanSlot &nx = L.slot[cs ^ 1];
                             if (nx.sid < p.n && nx.rows > 0) {
@@ -623,12 +639,16 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
                                 }
                             }
                         }
-                        const uint32_t tail = (cur == nvec - 1) ? (len & 15) : 0;
-                        uint4 r[4];
-                        column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
+                        if (cur < nvec) {
+                            const uint32_t tail = (cur == nvec - 1) ? (len & 15) : 0;
+                            uint4 r[4];
+                            column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            if (i < rows) stg_stream(dbase + ps.dst_off[i] + (size_t)cur * 16, r[i]);
+                            for (int i = 0; i < 4; i++)
+                                if (i < rows) stg_stream(dbase + ps.dst_off[i] + (size_t)cur * 16, r[i]);
+                        }
+                        chunk = nxt;
+                        nxt = __shfl_sync(0xffffffffu, nxt2, 0);
                     }
                 } else {
                     for (; col < nvec; col += kThreads) {
