@@ -83,7 +83,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.reasons = index, [], set()
-        self.max_mhz, self.err = None, None
+        self.max_mhz, self.err, self.raw_mask, self.power_w = None, None, 0, []
         try:
             import pynvml
 
@@ -98,22 +98,23 @@ class ClockSampler:
         nv = self.nv
         if not nv:
             return
-        names = {
-            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
-            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
-            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
-        }
+        names = {"gpu_idle": 0x1, "applications_clocks_setting": 0x2, "sw_power_cap": 0x4, "hw_slowdown": 0x8,
+                 "sync_boost": 0x10, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "display_clock_setting": 0x100}
         try:
             self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:  # older binding name
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.raw_mask |= int(r)
             for n, bit in names.items():
                 if r & bit:
                     self.reasons.add(n)
+            try:
+                self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
@@ -127,7 +128,11 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.err or "no samples"}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "reasons_raw_mask": self.raw_mask, "samples": len(self.samples),
+                "sm_mhz_min": min(self.samples), "sm_mhz_max_seen": max(self.samples),
+                "power_w_max": max(self.power_w) if self.power_w else None,
+                "note": "sampled by NVML while the timed steps execute; an HBM-bound kernel does not hold the SM "
+                        "clock at its maximum (DVFS), no clock lock is set by this program"}
 
 
 def alg_bytes_per_pass(k, m, e, n, L):
