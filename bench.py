@@ -290,29 +290,7 @@ def run_ours(args, rank, world, local_rank):
         step()
     barrier()
 
-    # ---- pass 1 (eager, per-kernel CUDA events recorded by the library on the launch stream):
-    # the kernel durations the roofline is computed from
-    enc.set_timing(True)
-    dec.set_timing(True)
-    enc.timing_read(), dec.timing_read()
-    l0 = enc.launch_count() + dec.launch_count()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ea.record()
-    for _ in range(args.steps):
-        step()
-    eb.record()
-    barrier()
-    eager_ms = ea.elapsed_time(eb)
-    launches = enc.launch_count() + dec.launch_count() - l0
-    enc_ms, enc_n = enc.timing_read()
-    dec_ms, dec_n = dec.timing_read()
-    enc.set_timing(False)
-    dec.set_timing(False)
-    assert int(status.abs().sum()) == 0
-    assert shards.view(torch.int64).sum().item() == orig_digest, "reconstruct digest mismatch"
-
-    # ---- pass 2 (the timed region of the headline): the same K steps with the host out of the way.
+    # ---- the timed region of the headline: K steps with the host out of the way.
     # One step (the same two library calls) is captured into a CUDA graph -- the DEVICE entry points
     # only enqueue kernels and stream-ordered allocations -- and replayed K times; on the eager pass
     # the Python/ctypes/driver path left 30-140 us of launch gaps per 1.9 ms step depending on the
@@ -347,9 +325,33 @@ def run_ours(args, rank, world, local_rank):
     # parity of the timed work: reconstructed shards == originals, parity unchanged
     assert int(status.abs().sum()) == 0
     assert shards.view(torch.int64).sum().item() == orig_digest, "reconstruct digest mismatch"
-    step_mode = {"mode": "cuda-graph replay of one captured step" if g_step is not None else "eager",
-                 "eager_ms_per_step_with_kernel_events": eager_ms / args.steps, "note": graph_note}
+    graph_used = g_step is not None
     del g_step
+
+    # ---- second pass (eager, per-kernel CUDA events recorded by the library on the launch stream):
+    # the kernel durations the roofline is computed from, same K steps, same inputs
+    enc.set_timing(True)
+    dec.set_timing(True)
+    enc.timing_read(), dec.timing_read()
+    l0 = enc.launch_count() + dec.launch_count()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ea.record()
+    for _ in range(args.steps):
+        step()
+    eb.record()
+    barrier()
+    eager_ms = ea.elapsed_time(eb)
+    launches = enc.launch_count() + dec.launch_count() - l0
+    enc_ms, enc_n = enc.timing_read()
+    dec_ms, dec_n = dec.timing_read()
+    enc.set_timing(False)
+    dec.set_timing(False)
+    assert int(status.abs().sum()) == 0
+    assert shards.view(torch.int64).sum().item() == orig_digest, "reconstruct digest mismatch"
+
+    step_mode = {"mode": "cuda-graph replay of one captured step" if graph_used else "eager",
+                 "eager_ms_per_step_with_kernel_events": eager_ms / args.steps, "note": graph_note}
 
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
