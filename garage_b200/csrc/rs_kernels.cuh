@@ -682,14 +682,14 @@ struct PlanParams {
     uint32_t *counter;       // reset to 0 for the apply kernel's scheduler
     uint32_t n, k, m;
     uint32_t present_is_bad;  // 1: `present` holds "bad" flags (scrub): a shard is present iff flag == 0
-    uint8_t P[kMaxM * kMaxK];  // parity rows, P[i*k + j]
+    alignas(16) uint8_t P[kMaxM * kMaxK];  // parity rows, P[i*k + j] (16-byte aligned: staged with uint4 loads)
 };
 
 constexpr int kPlanWarps = 4;
 
-// One warp per stripe: pick the first k present shards, invert the k x k submatrix of
-// [I;P] they form (Gauss-Jordan, lanes own columns), compose the rows that map the
-// survivors straight to every wanted absent shard.
+// One warp per stripe: pick the first k present shards, solve the a x a system that couples the
+// a absent data shards to the a parity survivors (Gauss-Jordan, lanes own columns), compose the
+// rows that map the survivors straight to every wanted absent shard.
 __global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_constant__ PlanParams q)
 {
     __shared__ __align__(16) uint8_t s_gf[sizeof(GfTables)];
@@ -698,8 +698,17 @@ __global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_c
     __shared__ uint8_t s_surv[kPlanWarps][kMaxK];
     __shared__ uint8_t s_out[kPlanWarps][kMaxM];
     __shared__ uint8_t s_col[kPlanWarps][kMaxK];
+    __shared__ uint8_t s_dm[kPlanWarps][kMaxM];
+    __shared__ __align__(16) uint8_t s_P[kMaxM * kMaxK];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_gf_tables(s_gf);
+    {  // parity rows: kernel parameter (constant bank) -> shared, warp-uniform 16-byte loads
+        const uint4 *src = reinterpret_cast<const uint4 *>(q.P);
+        for (uint32_t i = warp; i < sizeof(q.P) / 16; i += blockDim.x >> 5) {
+            const uint4 v = src[i];
+            if (lane < 4) reinterpret_cast<uint32_t *>(s_P)[i * 4 + lane] = lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
+        }
+    }
     if (blockIdx.x == 0 && tid == 0) *q.counter = 0;
     __syncthreads();
     auto mul = [&](uint32_t a, uint32_t b) -> uint32_t {
@@ -752,65 +761,89 @@ __global__ void __launch_bounds__(kPlanWarps * 32) rs_plan_kernel(const __grid_c
     __syncwarp();
     if (bad || nrows == 0) return;
 
-    // A = [S | I], S[r][c] = generator row surv[r]
-    uint8_t(*A)[2 * kMaxK] = s_A[warp];
-    for (uint32_t r = 0; r < k; r++) {
-        const uint32_t g = s_surv[warp][r];
-        for (uint32_t c = lane; c < 2 * k; c += 32) {
-            uint8_t v;
-            if (c < k) v = g < k ? (uint8_t)(g == c) : q.P[(g - k) * k + c];
-            else v = (uint8_t)(c - k == r);
-            A[r][c] = v;
+    // The survivors are the present data shards (identity rows of the generator) followed by the
+    // first `a` present parity shards, a = number of absent data shards.  Only an a x a system
+    // couples the unknowns:   y_Pu = A x_Dm + B x_Dp,   A = P[Pu][Dm], B = P[Pu][Dp]
+    //   =>  x_Dm = Ainv y_Pu + (Ainv B) x_Dp          (characteristic 2)
+    // so a full k x k inversion is never needed (a <= m <= 8).
+    uint8_t(*A)[2 * kMaxK] = s_A[warp];  // rows 0..7: [A | I] -> [I | Ainv]; rows 8..15: Ainv*B; rows 16..23: decode rows
+    const unsigned long long datamask = (k >= 64 ? ~0ull : ((1ull << k) - 1));
+    const unsigned long long mdmask = ~present & datamask;
+    const uint32_t a = (uint32_t)__popcll(mdmask);
+    const uint32_t nd = k - a;  // data survivors occupy positions [0, nd) of surv[], parity survivors [nd, k)
+    if (lane == 0) {
+        unsigned long long mm = mdmask;
+        for (uint32_t t = 0; t < a; t++) {
+            s_dm[warp][t] = (uint8_t)(__ffsll((long long)mm) - 1);
+            mm &= mm - 1;
         }
     }
     __syncwarp();
-    for (uint32_t c = 0; c < k; c++) {
-        // pivot search: lanes are rows
-        const bool cand = lane < k && lane >= c && A[lane][c] != 0;
-        const uint32_t bal = __ballot_sync(0xffffffffu, cand);
-        if (!bal) {  // singular: cannot happen for an MDS generator; report unrecoverable
-            if (lane == 0) {
-                pl->nrows = 0;
-                pl->unrecoverable = 1;
-                if (q.status) q.status[s] = -4;
-            }
-            return;
-        }
-        const uint32_t piv = __ffs(bal) - 1;
-        const uint32_t iv = s_exp[255 - s_log[A[piv][c]]];
-        __syncwarp();
-        for (uint32_t x = lane; x < 2 * k; x += 32) {
-            const uint8_t a = A[piv][x], b = A[c][x];
-            A[piv][x] = b;                   // swap (no-op when piv == c)
-            A[c][x] = (uint8_t)mul(a, iv);   // scaled pivot row
+    if (a) {
+        for (uint32_t r = 0; r < a; r++) {
+            const uint32_t prow = (uint32_t)s_surv[warp][nd + r] - k;
+            if (lane < 2 * a) A[r][lane] = lane < a ? s_P[prow * k + s_dm[warp][lane]] : (uint8_t)(lane - a == r);
         }
         __syncwarp();
-        // eliminate column c from every other row: lanes own columns; the k row factors are
-        // copied out of column c first (lane c is about to overwrite it)
-        const uint32_t p0v = lane < 2 * k ? A[c][lane] : 0, p1v = lane + 32 < 2 * k ? A[c][lane + 32] : 0;
-        const uint32_t lp0 = s_log[p0v], lp1 = s_log[p1v];
-        if (lane < k) s_col[warp][lane] = lane == c ? 0 : A[lane][c];
-        __syncwarp();
-        for (uint32_t r = 0; r < k; r++) {
-            const uint32_t f = s_col[warp][r];  // broadcast
-            if (f) {                            // warp-uniform
-                const uint32_t lf = s_log[f];
-                if (p0v) A[r][lane] ^= s_exp[lf + lp0];
-                if (p1v) A[r][lane + 32] ^= s_exp[lf + lp1];
+        for (uint32_t c = 0; c < a; c++) {
+            const bool cand = lane < a && lane >= c && A[lane][c] != 0;  // pivot search: lanes are rows
+            const uint32_t bal = __ballot_sync(0xffffffffu, cand);
+            if (!bal) {  // singular: cannot happen for an MDS generator; report unrecoverable
+                if (lane == 0) {
+                    pl->nrows = 0;
+                    pl->unrecoverable = 1;
+                    if (q.status) q.status[s] = -4;
+                }
+                return;
             }
+            const uint32_t piv = __ffs(bal) - 1;
+            const uint32_t iv = s_exp[255 - s_log[A[piv][c]]];
+            __syncwarp();
+            if (lane < 2 * a) {
+                const uint8_t x = A[piv][lane], y = A[c][lane];
+                A[piv][lane] = y;                  // swap (no-op when piv == c)
+                A[c][lane] = (uint8_t)mul(x, iv);  // scaled pivot row
+            }
+            __syncwarp();
+            const uint32_t pv = lane < 2 * a ? A[c][lane] : 0;
+            if (lane < a) s_col[warp][lane] = lane == c ? 0 : A[lane][c];
+            __syncwarp();
+            for (uint32_t r = 0; r < a; r++) {
+                const uint32_t f = s_col[warp][r];  // broadcast; lanes own columns
+                if (f && lane < 2 * a) A[r][lane] ^= (uint8_t)mul(f, pv);
+            }
+            __syncwarp();
+        }
+        // decode row of missing data shard dm[t] over the survivor positions:
+        //   data survivors:   (Ainv B)[t][j] = XOR_r Ainv[t][r] * P[Pu_r][surv[j]]
+        //   parity survivors: Ainv[t][j - nd]
+        for (uint32_t t = 0; t < a; t++) {
+            uint32_t v = 0;
+            if (lane < nd) {
+                const uint32_t col = s_surv[warp][lane];
+                for (uint32_t r = 0; r < a; r++)
+                    v ^= mul(A[t][a + r], s_P[((uint32_t)s_surv[warp][nd + r] - k) * k + col]);
+            } else if (lane < k) {
+                v = A[t][a + (lane - nd)];
+            }
+            if (lane < k) A[16 + t][lane] = (uint8_t)v;
         }
         __syncwarp();
     }
-    // inverse now in A[:, k..2k).  Compose rows for the outputs.
+    // rows for the wanted outputs
     for (int r = 0; r < nrows; r++) {
         const uint32_t o = s_out[warp][r];
         if (lane < k) {
-            uint32_t v;
+            uint32_t v = 0;
             if (o < k) {
-                v = A[o][k + lane];
+                // rank of o among the absent data shards
+                const uint32_t t = (uint32_t)__popcll(mdmask & ((1ull << o) - 1));
+                v = A[16 + t][lane];
             } else {
-                v = 0;
-                for (uint32_t x = 0; x < k; x++) v ^= mul(q.P[(o - k) * k + x], A[x][k + lane]);
+                // absent parity row i: P[i][Dp] on the data survivors, plus P[i][Dm] through the rows above
+                const uint32_t i = o - k;
+                if (lane < nd) v = s_P[i * k + s_surv[warp][lane]];
+                for (uint32_t t = 0; t < a; t++) v ^= mul(s_P[i * k + s_dm[warp][t]], A[16 + t][lane]);
             }
             pl->coef[r][lane] = (uint8_t)v;
         }
