@@ -96,3 +96,13 @@ def test_product_does_not_touch_oracle():
                     assert not re.search(pat, txt, flags=re.M), (f, pat)
     out = subprocess.run(["ldd", G.lib_path()], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_rust_shim_declares_every_symbol():
+    """integration/garage_block_cuda/src/sys.rs (source only: no rustc here) must bind exactly
+    the symbols the header declares"""
+    src = open(os.path.join(ROOT, "integration", "garage_block_cuda", "src", "sys.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (garage_ec_[a-z0-9_]+)\s*\(", src)))
+    assert rust == header_decls()
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert sorted(set(re.findall(r"pub fn (garage_ec_[a-z0-9_]+)\s*\(", md))) == header_decls()
