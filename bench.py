@@ -329,7 +329,13 @@ def run_ours(args, rank, world, local_rank):
     del g_step
 
     # ---- second pass (eager, per-kernel CUDA events recorded by the library on the launch stream):
-    # the kernel durations the roofline is computed from, same K steps, same inputs
+    # the kernel durations the roofline is computed from, same K steps, same inputs.  A short pause
+    # and fresh warm-up steps first: straight after ~100 ms of sustained load the SM/memory clocks
+    # of some boxes sag (DVFS, no throttle reason reported) and the second region measured 2-4 % slow.
+    time.sleep(1.0)
+    for _ in range(3):
+        step()
+    barrier()
     enc.set_timing(True)
     dec.set_timing(True)
     enc.timing_read(), dec.timing_read()
