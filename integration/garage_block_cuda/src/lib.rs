@@ -53,6 +53,8 @@ impl ErasureCoder {
         let tot = self.k + self.m;
         let l = self.shard_len(block_len);
         let stride = unsafe { sys::garage_ec_stride_for(l as u32) };
+        // the C ABI wants 16-byte aligned bases: glibc's allocator gives that for a Vec<u8> of this size;
+        // production code takes these buffers from garage_ec_host_alloc (pinned, page aligned)
         let mut buf = vec![0u8; tot * stride];
         let mut present = vec![0u8; tot];
         for (i, s) in shards.iter().enumerate() {
