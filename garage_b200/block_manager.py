@@ -16,6 +16,7 @@ SYMBOLS = [
     "garage_bm_rpc_put_block", "garage_bm_rpc_get_block", "garage_bm_resync_block", "garage_bm_resync_all",
     "garage_bm_repair_enqueue_missing", "garage_bm_scrub", "garage_bm_set_node_up", "garage_bm_corrupt_shard",
     "garage_bm_drop_shard", "garage_bm_node_shard_index", "garage_bm_storage_nodes_of", "garage_bm_get_metrics",
+    "garage_bm_block_incref", "garage_bm_block_decref", "garage_bm_get_block_rc",
 ]
 
 
@@ -52,6 +53,10 @@ def load_library():
         L.garage_bm_rpc_put_block.argtypes = [vp, vp, vp, sz]
         L.garage_bm_rpc_get_block.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
         L.garage_bm_resync_block.argtypes = [vp, i32, vp]
+        L.garage_bm_block_incref.argtypes = [vp, vp]
+        L.garage_bm_block_decref.argtypes = [vp, vp]
+        L.garage_bm_get_block_rc.argtypes = [vp, vp]
+        L.garage_bm_get_block_rc.restype = C.c_longlong
         L.garage_bm_resync_all.argtypes = [vp, i32, i32, C.POINTER(C.c_uint64)]
         L.garage_bm_repair_enqueue_missing.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
         L.garage_bm_scrub.argtypes = [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -130,6 +135,15 @@ class BlockManager:
         n = C.c_size_t(0)
         rc = self._L.garage_bm_rpc_get_block(self._h, self._hp(hash32), C.c_void_p(out.ctypes.data), cap, C.byref(n))
         return rc, (out[: n.value].copy() if rc == OK else None)
+
+    def block_incref(self, hash32):
+        return self._L.garage_bm_block_incref(self._h, self._hp(hash32))
+
+    def block_decref(self, hash32):
+        return self._L.garage_bm_block_decref(self._h, self._hp(hash32))
+
+    def get_block_rc(self, hash32):
+        return int(self._L.garage_bm_get_block_rc(self._h, self._hp(hash32)))
 
     def resync_block(self, node, hash32):
         return self._L.garage_bm_resync_block(self._h, node, self._hp(hash32))

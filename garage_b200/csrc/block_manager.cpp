@@ -398,6 +398,9 @@ struct garage_bm {
     // which blocks exist and how long they are
     std::mutex refs_mu;
     std::unordered_map<Hash, uint32_t, HashHasher> refs;
+    // block reference counts (src/block/rc.rs): only blocks that went through block_incref /
+    // block_decref have an entry; a block without entry is treated as needed (rc > 0)
+    std::unordered_map<Hash, int64_t, HashHasher> rc;
     std::unique_ptr<ByteSemaphore> ram;
     std::unique_ptr<Batcher<EncodeItem>> enc_batcher;
     std::unique_ptr<Batcher<ReconItem>> rec_batcher;
@@ -662,16 +665,25 @@ struct garage_bm {
         for (int i = 0; i < tot; i++)
             if (who[i] == node) idx = i;
         if (idx < 0) return GARAGE_BM_OK;  // not a storage node for it any more (resync.rs:466-477)
+        bool known, deletable;
         {
             std::lock_guard<std::mutex> lk(refs_mu);
-            if (!refs.count(h)) return GARAGE_BM_OK;  // rc == 0: nothing to fetch
+            known = refs.count(h) != 0;
+            auto it = rc.find(h);
+            deletable = it != rc.end() && it->second <= 0;  // rc.is_deletable() (rc.rs)
         }
         {
             Node &nd = *nodes[node];
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return GARAGE_BM_E_MESSAGE;
-            if (nd.store_has(h)) return GARAGE_BM_OK;  // exists
+            const bool exists = nd.store_has(h);
+            if (exists && deletable) {  // offload branch, resync.rs:369-458: nobody needs it -> delete_if_unneeded
+                if (nd.store_erase(h)) delete_counter++;
+                return GARAGE_BM_OK;
+            }
+            if (exists) return GARAGE_BM_OK;
         }
+        if (!known || deletable) return GARAGE_BM_OK;  // rc == 0: nothing to fetch
         std::vector<StoredShard> got;
         std::vector<uint8_t> have;
         uint32_t block_len = 0;
@@ -699,6 +711,48 @@ struct garage_bm {
         write_shard(node, h, idx, block_len, it.rebuilt[idx].data(), it.rebuilt[idx].size(), sum);  // resync.rs:499
         resync_counter++;
         return GARAGE_BM_OK;
+    }
+
+    // BlockManager::block_incref / block_decref (manager.rs:452-500), driven in Garage by
+    // BlockRefTable::updated (src/model/s3/block_ref_table.rs:69-85): a 0 -> 1 transition queues a
+    // resync on every storage node of the block (safety check that the shard really arrives), a
+    // drop to 0 queues one too (so that the shard gets deleted).
+    void block_incref(const Hash &h)
+    {
+        bool first;
+        {
+            std::lock_guard<std::mutex> lk(refs_mu);
+            int64_t &c = rc[h];
+            first = c <= 0;
+            c = first ? 1 : c + 1;
+        }
+        if (first) queue_on_storage_nodes(h);
+    }
+    void block_decref(const Hash &h)
+    {
+        bool zero = false;
+        {
+            std::lock_guard<std::mutex> lk(refs_mu);
+            auto it = rc.find(h);
+            if (it == rc.end()) it = rc.emplace(h, 1).first;  // an un-counted block counts as referenced once
+            if (it->second > 0 && --it->second == 0) {
+                zero = true;
+                refs.erase(h);
+            }
+        }
+        if (zero) queue_on_storage_nodes(h);
+    }
+    void queue_on_storage_nodes(const Hash &h)
+    {
+        int who[64];
+        storage_nodes_of(h, who);
+        for (int i = 0; i < tot; i++) put_to_resync(who[i], h);
+    }
+    int64_t get_block_rc(const Hash &h)
+    {
+        std::lock_guard<std::mutex> lk(refs_mu);
+        auto it = rc.find(h);
+        return it == rc.end() ? -1 : it->second;
     }
 
     int resync_all(int node, int workers, uint64_t *resynced)
@@ -947,6 +1001,26 @@ int garage_bm_resync_block(garage_bm *bm, int node, const uint8_t hash[32])
 {
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
     return bm->resync_block(node, to_hash(hash));
+}
+
+int garage_bm_block_incref(garage_bm *bm, const uint8_t hash[32])
+{
+    if (!bm || !hash) return GARAGE_EC_E_INVALID;
+    bm->block_incref(to_hash(hash));
+    return GARAGE_BM_OK;
+}
+
+int garage_bm_block_decref(garage_bm *bm, const uint8_t hash[32])
+{
+    if (!bm || !hash) return GARAGE_EC_E_INVALID;
+    bm->block_decref(to_hash(hash));
+    return GARAGE_BM_OK;
+}
+
+long long garage_bm_get_block_rc(garage_bm *bm, const uint8_t hash[32])
+{
+    if (!bm || !hash) return -1;
+    return (long long)bm->get_block_rc(to_hash(hash));
 }
 
 int garage_bm_resync_all(garage_bm *bm, int node, int workers, uint64_t *resynced)

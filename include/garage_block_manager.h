@@ -83,7 +83,16 @@ int garage_bm_rpc_put_block(garage_bm *bm, const uint8_t hash[32], const uint8_t
 int garage_bm_rpc_get_block(garage_bm *bm, const uint8_t hash[32], uint8_t *out, size_t cap,
                             size_t *out_len);
 
-/* resync.rs:354-503, fetch branch, for storage node `node`.                                     */
+/* manager.rs:452-500 block_incref / block_decref (called by BlockRefTable::updated,
+ * src/model/s3/block_ref_table.rs:69-85): 0 -> 1 and 1 -> 0 transitions queue a resync on every
+ * storage node of the block; get_block_rc (manager.rs:421-449) returns -1 for a block that was
+ * never counted (treated as referenced).                                                        */
+int garage_bm_block_incref(garage_bm *bm, const uint8_t hash[32]);
+int garage_bm_block_decref(garage_bm *bm, const uint8_t hash[32]);
+long long garage_bm_get_block_rc(garage_bm *bm, const uint8_t hash[32]);
+
+/* resync.rs:354-503 for storage node `node`: fetch branch (rc > 0, shard absent: rebuild it from k
+ * survivors) and the deletion half of the offload branch (rc == 0, shard present: delete it).   */
 int garage_bm_resync_block(garage_bm *bm, int node, const uint8_t hash[32]);
 /* drain node's resync queue with `workers` concurrent workers (resync.rs:43: up to 8);
  * returns the number of blocks that could not be resynced (they stay queued, with backoff

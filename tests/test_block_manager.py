@@ -239,3 +239,35 @@ def test_file_backed_store_survives_restart(tmp_path):
         assert bm.resync_all(who[1]) == (0, 1)
         rc, checked, corrupt = bm.scrub(who[1])
         assert (rc, corrupt) == (BM.OK, 0) and checked >= 1
+
+
+@pytest.mark.gpu
+def test_refcount_drives_resync_and_deletion():
+    """block_incref / block_decref (manager.rs:452-500): 0 -> 1 queues a safety resync everywhere,
+    the last decref queues the deletion; resync then deletes the shard (delete_if_unneeded)."""
+    k, m = 4, 2
+    b = O.fill_random(300000, 9)
+    with BM.BlockManager(k, m) as bm:
+        h = BM.blake2sum(b)
+        assert bm.get_block_rc(h) == -1
+        bm.block_incref(h)                      # BlockRefTable::updated on insert
+        assert bm.get_block_rc(h) == 1 and bm.metrics()["resync_queue_length"] == k + m
+        assert bm.rpc_put_block(h, b) == BM.OK
+        for node in range(k + m):                # the safety resync finds every shard in place
+            assert bm.resync_all(node) == (0, 1)
+        bm.block_incref(h)
+        bm.block_decref(h)
+        assert bm.get_block_rc(h) == 1 and bm.metrics()["resync_queue_length"] == 0
+        # a lost shard of a referenced block is rebuilt ...
+        who = bm.storage_nodes_of(h)
+        assert bm.drop_shard(who[0], h) == BM.OK
+        assert bm.resync_block(who[0], h) == BM.OK and bm.node_shard_index(who[0], h) == 0
+        # ... and after the last decref every node deletes its shard
+        bm.block_decref(h)
+        assert bm.get_block_rc(h) == 0 and bm.metrics()["resync_queue_length"] == k + m
+        for node in range(k + m):
+            assert bm.resync_all(node) == (0, 1)
+            assert bm.node_shard_index(node, h) == -1
+        rc, _ = bm.rpc_get_block(h)
+        assert rc == BM.E_MISSING_BLOCK
+        assert bm.metrics()["delete_counter"] == k + m + 1  # + the drop_shard above
