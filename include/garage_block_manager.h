@@ -18,6 +18,7 @@
  *                           (per-shard blake2sum; corrupt -> quarantine + resync queue)
  *   ScrubWorker             src/block/repair.rs:438-490    (sweep of one node's shards)
  *   write_block             src/block/manager.rs:517-530, 720-805 (local durable store)
+ *   block_incref/decref     src/block/manager.rs:452-500, get_block_rc :421-449 (src/block/rc.rs)
  *   batching front-end      (row f1) concurrent PUT / resync calls coalesced into GPU batches,
  *                           back-pressure like buffer_kb_semaphore (manager.rs:156,380-385)
  */
