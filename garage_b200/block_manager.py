@@ -16,7 +16,7 @@ SYMBOLS = [
     "garage_bm_rpc_put_block", "garage_bm_rpc_get_block", "garage_bm_resync_block", "garage_bm_resync_all",
     "garage_bm_repair_enqueue_missing", "garage_bm_scrub", "garage_bm_set_node_up", "garage_bm_corrupt_shard",
     "garage_bm_drop_shard", "garage_bm_node_shard_index", "garage_bm_storage_nodes_of", "garage_bm_get_metrics",
-    "garage_bm_block_incref", "garage_bm_block_decref", "garage_bm_get_block_rc",
+    "garage_bm_block_incref", "garage_bm_block_decref", "garage_bm_get_block_rc", "garage_bm_scrub_step",
 ]
 
 
@@ -60,6 +60,7 @@ def load_library():
         L.garage_bm_resync_all.argtypes = [vp, i32, i32, C.POINTER(C.c_uint64)]
         L.garage_bm_repair_enqueue_missing.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
         L.garage_bm_scrub.argtypes = [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.garage_bm_scrub_step.argtypes = [vp, i32, vp, sz, vp, C.POINTER(i32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.garage_bm_set_node_up.argtypes = [vp, i32, i32]
         L.garage_bm_corrupt_shard.argtypes = [vp, i32, vp, sz]
         L.garage_bm_drop_shard.argtypes = [vp, i32, vp]
@@ -162,6 +163,14 @@ class BlockManager:
         a, b = C.c_uint64(0), C.c_uint64(0)
         rc = self._L.garage_bm_scrub(self._h, node, C.byref(a), C.byref(b))
         return rc, a.value, b.value
+
+    def scrub_step(self, node, cursor=None, max_shards=0):
+        """-> (rc, cursor_out bytes, finished, checked, corrupt)"""
+        out = C.create_string_buffer(32)
+        fin, a, b = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        rc = self._L.garage_bm_scrub_step(self._h, node, C.c_char_p(bytes(cursor)) if cursor else None, max_shards,
+                                          C.cast(out, C.c_void_p), C.byref(fin), C.byref(a), C.byref(b))
+        return rc, out.raw, bool(fin.value), a.value, b.value
 
     def set_node_up(self, node, up):
         return self._L.garage_bm_set_node_up(self._h, node, 1 if up else 0)

@@ -819,7 +819,13 @@ struct garage_bm {
     }
 
     // ScrubWorker sweep of one node (repair.rs:438-490) with the GPU doing the hashing
-    int scrub(int node, uint64_t *checked, uint64_t *corrupt)
+    // `cursor`/`max_shards`: the scrub iterator checkpoint of the reference (ScrubWorker persists
+    // its BlockStoreIterator position every 60 s, repair.rs:186-193,460-464, so a sweep survives a
+    // restart): shards are visited in hash order, starting after *cursor (NULL = from the start),
+    // at most max_shards of them (0 = all); *cursor_out receives the last hash visited and
+    // *finished whether the end of the store was reached.
+    int scrub(int node, uint64_t *checked, uint64_t *corrupt, const Hash *cursor = nullptr, size_t max_shards = 0,
+              Hash *cursor_out = nullptr, int *finished = nullptr)
     {
         std::lock_guard<std::mutex> sl(scrub_mu);
         Node &nd = *nodes[node];
@@ -828,6 +834,19 @@ struct garage_bm {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return GARAGE_BM_E_MESSAGE;
             nd.store_list(hashes);
+        }
+        std::sort(hashes.begin(), hashes.end());
+        if (cursor) hashes.erase(hashes.begin(), std::upper_bound(hashes.begin(), hashes.end(), *cursor));
+        bool done = true;
+        if (max_shards && hashes.size() > max_shards) {
+            hashes.resize(max_shards);
+            done = false;
+        }
+        if (finished) *finished = done ? 1 : 0;
+        if (cursor_out) {
+            if (!hashes.empty()) *cursor_out = hashes.back();
+            else if (cursor) *cursor_out = *cursor;
+            else cursor_out->fill(0);
         }
         uint64_t nchecked = 0, nbad = 0;
         const size_t chunk = std::max<size_t>(1, (size_t)cfg.batch_max_blocks * tot);
@@ -1039,6 +1058,17 @@ int garage_bm_scrub(garage_bm *bm, int node, uint64_t *checked, uint64_t *corrup
 {
     if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
     return bm->scrub(node, checked, corrupt);
+}
+
+int garage_bm_scrub_step(garage_bm *bm, int node, const uint8_t *cursor32, size_t max_shards, uint8_t cursor_out32[32],
+                         int *finished, uint64_t *checked, uint64_t *corrupt)
+{
+    if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
+    Hash cur, out;
+    if (cursor32) cur = to_hash(cursor32);
+    int rc = bm->scrub(node, checked, corrupt, cursor32 ? &cur : nullptr, max_shards, &out, finished);
+    if (rc == GARAGE_BM_OK && cursor_out32) memcpy(cursor_out32, out.data(), 32);
+    return rc;
 }
 
 int garage_bm_set_node_up(garage_bm *bm, int node, int up)

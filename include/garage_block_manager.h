@@ -106,6 +106,12 @@ int garage_bm_repair_enqueue_missing(garage_bm *bm, int node, uint64_t *enqueued
  * shard; a mismatch quarantines the shard (.corrupted, manager.rs:807-819) and queues a resync
  * (manager.rs:592-605).                                                                         */
 int garage_bm_scrub(garage_bm *bm, int node, uint64_t *checked, uint64_t *corrupt);
+/* the same sweep in resumable steps -- the scrub checkpoint of the reference (ScrubWorker persists its
+ * BlockStoreIterator position every 60 s, repair.rs:186-193,460-464): shards are visited in hash order
+ * starting after cursor32 (NULL = from the start), at most max_shards (0 = all); cursor_out32 is the
+ * position to persist, *finished = 1 once the end of the node's store was reached.                */
+int garage_bm_scrub_step(garage_bm *bm, int node, const uint8_t *cursor32, size_t max_shards,
+                         uint8_t cursor_out32[32], int *finished, uint64_t *checked, uint64_t *corrupt);
 
 /* fault injection / inspection for tests */
 int garage_bm_set_node_up(garage_bm *bm, int node, int up);

@@ -271,3 +271,30 @@ def test_refcount_drives_resync_and_deletion():
         rc, _ = bm.rpc_get_block(h)
         assert rc == BM.E_MISSING_BLOCK
         assert bm.metrics()["delete_counter"] == k + m + 1  # + the drop_shard above
+
+
+@pytest.mark.gpu
+def test_scrub_is_resumable_from_a_checkpoint():
+    """ScrubWorker checkpoints its iterator (repair.rs:186-193,460-464): scrub_step visits shards in
+    hash order from a cursor, so a sweep can be cut in pieces (or survive a restart) and still see every
+    shard exactly once."""
+    k, m, nblocks = 4, 2, 23
+    blocks = [O.fill_random(50000 + 1000 * i, 400 + i) for i in range(nblocks)]
+    with BM.BlockManager(k, m) as bm:
+        hashes = put_all(bm, blocks)
+        node = 2
+        bm.corrupt_shard(node, hashes[5], 3)
+        bm.corrupt_shard(node, hashes[17], 9)
+        cursor, total, bad, steps = None, 0, 0, 0
+        while True:
+            rc, cursor, finished, checked, corrupt = bm.scrub_step(node, cursor, max_shards=7)
+            assert rc == BM.OK and checked <= 7
+            total += checked
+            bad += corrupt
+            steps += 1
+            if finished:
+                break
+        assert (total, bad, steps) == (nblocks, 2, 4)
+        assert bm.metrics()["resync_queue_length"] == 2
+        rc, cursor2, finished, checked, corrupt = bm.scrub_step(node, cursor, max_shards=7)
+        assert finished and checked == 0 and cursor2 == cursor  # nothing after the last checkpoint
