@@ -456,6 +456,9 @@ def run_ours(args, rank, world, local_rank):
                 "blocks_per_gpu": n, "shard_len": L, "stride": stride, "matrix": "vandermonde-systematic",
                 "l2": "inputs larger than L2 (%.1f GB per pass vs 126 MB), no flush needed" % (enc_alg / 1e9),
                 "parallelism": "independent block ranges per GPU, NCCL broadcast of matrix+ranges only" if world > 1 else "1 GPU",
+                "timed_region": "K steps = K replays of a CUDA graph holding one step's library calls (garage_ec_encode + "
+                                "garage_ec_reconstruct, DEVICE mode): every replay re-executes all kernels on the same "
+                                "device-resident inputs; per-kernel CUDA events come from an eager pass of the same K steps",
             },
             "encode_gibs": n * B * world / (enc_avg_ms * 1e-3) / GIB,
             "decode_gibs": n * B * world / (dec_avg_ms * 1e-3) / GIB,
