@@ -43,7 +43,6 @@ struct garage_ec_ctx {
     uint8_t P[kMaxM * kMaxK] = {0};
     int sm_count = 0;
     size_t smem_optin = 0;
-    size_t smem_bytes = 0;
     std::mutex host_mu;  // serialises HOST-mode calls (they share the lanes)
     HostLane lanes[kHostLanes];
     std::mutex misc_mu;  // timing list, last_error
@@ -114,38 +113,23 @@ struct TimedLaunch {
 };
 
 // ---- kernel dispatch --------------------------------------------------------------------
-// Launch shape per (mode, K), tuned on B200 (profiles/r01_summary.md): few sources per column
-// leave registers for more warps (latency hiding); k >= 9 wants 512 fat threads with prefetch.
-template <int MODE, int K> struct LaunchShape {
-    static constexpr int NT = (GEC_NT_ENC != 512) ? GEC_NT_ENC
-                              : (K == 0 ? 512 : (K <= 4 ? 1024 : (K <= 6 ? 768 : (K <= 8 ? 640 : 512))));
-    static constexpr bool PIPE = GEC_PIPE_ENC && slots_for_k(K > 0 ? K : 1) <= 12;  // 2 x slots x 4 registers
-};
-template <int K> struct LaunchShape<kModePlan, K> {
-    static constexpr int NT = (GEC_NT_PLAN != 512) ? GEC_NT_PLAN
-                              : (K == 0 ? 512 : (K <= 4 ? 1024 : (K <= 6 ? 768 : (K <= 8 ? 640 : 512))));
-    static constexpr bool PIPE = GEC_PIPE_PLAN && slots_for_k(K > 0 ? K : 1) <= 12;
-};
-template <int K> struct LaunchShape<kModeVerify, K> {
-    static constexpr int NT = (GEC_NT_VER != 1024) ? GEC_NT_VER : ((K == 0 || K > 11) ? 512 : 1024);
-    static constexpr bool PIPE = GEC_PIPE_VER || (K > 0 && K <= 4);
-};
-
+// Launch shape, table layout and shared-memory carve-up are compile-time functions of (k, mode):
+// StreamCfg in rs_kernels.cuh.
 template <int K, int MODE>
 cudaError_t launch_apply_t(const garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t st)
 {
     static std::atomic<int> configured_for_device{-1};  // per instantiation
-    constexpr int NT = LaunchShape<MODE, K>::NT;
-    auto kern = rs_apply_kernel<K, MODE, NT, LaunchShape<MODE, K>::PIPE>;
+    using CFG = StreamCfg<K, MODE>;
+    auto kern = rs_apply_kernel<K, MODE>;
+    if ((size_t)CFG::kSmem > ctx->smem_optin) return cudaErrorInvalidConfiguration;
     // opt-in shared memory size is a per-function, per-device attribute; setting it is cheap
     // but not free, so remember the last device it was set for.
     if (configured_for_device.load(std::memory_order_acquire) != ctx->device) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ctx->smem_optin);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::kSmem);
         if (e != cudaSuccess) return e;
         configured_for_device.store(ctx->device, std::memory_order_release);
     }
-    kern<<<ctx->sm_count * GEC_MIN_BLOCKS, NT, ctx->smem_bytes, st>>>(p);
+    kern<<<ctx->sm_count, CFG::kThreads, CFG::kSmem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -154,14 +138,19 @@ cudaError_t launch_apply(garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t 
 {
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     switch (p.k) {
-#ifndef GEC_FAST_BUILD
 #define GEC_CASE(KK) case KK: return launch_apply_t<KK, MODE>(ctx, p, st);
+#ifndef GEC_FAST_BUILD
         GEC_CASE(1) GEC_CASE(2) GEC_CASE(3) GEC_CASE(4) GEC_CASE(5) GEC_CASE(6) GEC_CASE(7) GEC_CASE(8)
         GEC_CASE(9) GEC_CASE(11) GEC_CASE(12) GEC_CASE(13) GEC_CASE(14) GEC_CASE(15) GEC_CASE(16)
-#undef GEC_CASE
+        GEC_CASE(17) GEC_CASE(18) GEC_CASE(19) GEC_CASE(20) GEC_CASE(21) GEC_CASE(22) GEC_CASE(23) GEC_CASE(24)
+        GEC_CASE(25) GEC_CASE(26) GEC_CASE(27) GEC_CASE(28) GEC_CASE(29) GEC_CASE(30) GEC_CASE(31) GEC_CASE(32)
 #endif
-    case 10: return launch_apply_t<10, MODE>(ctx, p, st);
-    default: return launch_apply_t<0, MODE>(ctx, p, st);
+        GEC_CASE(10)
+#if defined(GEC_FAST_BUILD) && GEC_FAST_BUILD != 10
+        GEC_CASE(GEC_FAST_BUILD)
+#endif
+#undef GEC_CASE
+    default: return cudaErrorInvalidConfiguration;
     }
 }
 
@@ -352,11 +341,6 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    ctx->smem_bytes = smem_bytes_for(k);
-    if (ctx->smem_bytes > ctx->smem_optin) {
-        delete ctx;
-        return GARAGE_EC_E_NODEVICE;
-    }
     if (cudaSetDevice(device) != cudaSuccess) {
         delete ctx;
         return GARAGE_EC_E_NODEVICE;

@@ -13,78 +13,199 @@
 //  * HBM-bound byte work, no tensor cores.  The per-byte GF multiply-accumulate for up to 4
 //    output rows is ONE shared-memory lookup: T_j[x] = {C0j*x, C1j*x, C2j*x, C3j*x} packed in
 //    a 32-bit word, so a data byte costs one LDS + one XOR for all four rows.
-//  * Conflict-free lookups at 16 KB per table ("sub-warp interleaving").  Random byte indices
-//    into a plain 256-word table serialise ~3.5-way, lane-private replicas (32 KB/table) do
-//    not fit k = 10.  Instead G = 32/R tables share one 32 KB "group": table j = G*t + sub is
-//    replicated R times in banks [sub*R, sub*R + R) (word t*8192 + x*32 + sub*R + g).  The
-//    warp is cut in G sub-warps of R lanes; at any lookup instruction sub-warp q works on
-//    source G*t + (phase xor q), i.e. every sub-warp is in a different table of the group and
-//    every lane owns its bank: word = t*8192 + x*32 + (lane xor phase*R).  The source order is
-//    simply permuted per sub-warp when the data is LOADED (slot u holds source u xor q), which
-//    costs nothing because XOR-accumulation commutes.  RS(10,4): G = 2, 5 groups = 160 KB,
-//    1.0 wavefronts per LDS (the first version, plain R = 16 replication, measured 2.07).
-//  * log/antilog tables sit in __constant__ memory and are copied to shared memory; they are
-//    only used to BUILD the product tables (once per launch for encode/verify, once per
-//    change of erasure pattern for reconstruct), never in the streaming loop.
-//  * Streaming loop: one 16-byte column of all k shards per thread (coalesced 512 B per warp
-//    per shard, ld.global.nc.L1::no_allocate.v4), 16 lookups per shard, 4x4 byte transposes
-//    with PRMT, one 16-byte st.global.cs per output row; the next column's vectors are
-//    prefetched into registers while the current one is processed.
-//  * Persistent grid: one CTA per SM (tables fill shared memory), work items handed to warps
-//    (encode/verify) or to CTAs through an atomic counter (reconstruct).
+//  * Conflict-free lookups with small tables ("sub-warp interleaving", mixed group sizes).
+//    G tables share one 32 KB group: table `sub` of the group is replicated R = 32/G times in
+//    banks [sub*R, sub*R + R) of every 128-byte row x.  The warp is cut in G sub-warps of R
+//    lanes; at phase p of the group sub-warp q works on source base + (p xor q), so every
+//    sub-warp is in a different table and every lane owns its bank:
+//    word = group*8192 + x*32 + (lane xor p*R).  XOR accumulation commutes, so the per-lane
+//    source order costs nothing.  k sources are decomposed greedily into groups of 32/16/8/4/2/1
+//    tables (no padding lookups): RS(10,4) = one group of 8 + one group of 2 = 64 KB (round 1
+//    used uniform G = 2: 160 KB), k = 16 -> 32 KB, k = 32 -> 32 KB.
+//  * Two ways to bring a 16-byte column of every source to the lanes (StreamCfg::kTma):
+//      LDG  : k x ld.global.nc.v4 per lane straight into registers, the next column's vectors
+//             prefetched into a second register set (group size capped at 8 so that a warp
+//             instruction still reads >= 64 contiguous bytes per shard);
+//      TMA  : one elected lane issues k cp.async.bulk (1-D TMA) copies of 512 bytes -- the
+//             warp's 32 columns of each shard -- into the warp's private shared-memory stage
+//             and arms the stage's mbarrier with the byte count; the warp waits on the
+//             mbarrier, pulls its vectors with conflict-free LDS.128, and immediately re-arms
+//             the stage for its next work item, so the copy flies while the lookups run.  No
+//             prefetch registers, any lane may read any source row, which is what allows the
+//             16- and 32-table groups and k up to 32 at full speed.
+//  * Reconstruct (per-stripe matrices) runs WITHOUT block-wide barriers: two table buffers, a
+//    builder warp that stages the next stripe's plan and builds its tables while the consumer
+//    warps stream the current stripe, mbarriers `full[b]` (tables of buffer b ready) and
+//    `empty[b]` (every consumer warp has left the stripe that used buffer b).  Consumer warps
+//    claim 32-column chunks from a per-stripe shared counter and flow from stripe to stripe on
+//    their own.
+//  * log/antilog tables sit in __constant__ memory and are staged to shared memory by the
+//    decode-planning kernel; the product tables are built from xtime chains (no log lookups).
+//  * Persistent grid: one CTA per SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "blake2b.h"
 #include "gf256.h"
 
 namespace garage_ec {
 
-// Launch shapes per mode (1 CTA per SM; tables fill shared memory).  PIPE = prefetch the next
-// column's k vectors into registers while the current one is processed.  Tuned on B200
-// (profiles/r01_variants.md): encode/reconstruct like fewer, fatter threads with the prefetch;
-// verify (k+m loads per column, no stores) likes more threads.
-#ifndef GEC_NT_ENC
-#define GEC_NT_ENC 512
+// ---- tuning overrides (tools/build_variants.py); -1 = per-shape default -------------------
+#ifndef GEC_TMA_ENC
+#define GEC_TMA_ENC -1
 #endif
-#ifndef GEC_PIPE_ENC
-#define GEC_PIPE_ENC 1
+#ifndef GEC_TMA_PLAN
+#define GEC_TMA_PLAN -1
 #endif
-#ifndef GEC_NT_PLAN
-#define GEC_NT_PLAN 512
+#ifndef GEC_TMA_VER
+#define GEC_TMA_VER -1
 #endif
-#ifndef GEC_PIPE_PLAN
-#define GEC_PIPE_PLAN 1
+#ifndef GEC_NW_ENC
+#define GEC_NW_ENC 0  // consumer warps; 0 = default
 #endif
-#ifndef GEC_NT_VER
-#define GEC_NT_VER 1024
+#ifndef GEC_NW_PLAN
+#define GEC_NW_PLAN 0
 #endif
-#ifndef GEC_PIPE_VER
-#define GEC_PIPE_VER 0
+#ifndef GEC_NW_VER
+#define GEC_NW_VER 0
 #endif
+#ifndef GEC_TMA_FROM_K
+#define GEC_TMA_FROM_K 13  // encode / reconstruct use the TMA staging from this k on
+#endif
+
 constexpr int kMaxK = 32;
 constexpr int kMaxM = 8;
-constexpr int kRowsPerPass = 4;  // output rows packed in one 32-bit table word
+constexpr int kRowsPerPass = 4;          // output rows packed in one 32-bit table word
 constexpr uint32_t kGroupBytes = 32768;  // one table group: 256 rows x 32 banks x 4 B
+constexpr int kMaxGroups = 6;
+constexpr uint32_t kStageRowBytes = 512;  // 32 columns x 16 B of one shard
+constexpr uint32_t kSmemLimit = 227 * 1024;
 
-// tables per 32 KB group for k sources: smallest G (least padding) whose groups need <= 192 KB,
-// so that >= 32 KB of the SM's 228 KB stay L1 (with 224 KB of tables the global loads starve:
-// k = 7 measured 0.65 of peak against 0.92 for k = 6)
-#ifndef GEC_MIN_BLOCKS
-#define GEC_MIN_BLOCKS 1  // CTAs per SM the streaming kernel is sized for (tuning experiments only)
-#endif
-__host__ __device__ constexpr int log2_group_for_k(int k)
+enum ApplyMode { kModeEncode = 0, kModePlan = 1, kModeVerify = 2 };
+
+// ---- table layout: k sources -> groups of 2^lg tables ---------------------------------------
+struct TabLayout {
+    int nslots;   // >= k; slots >= k are zero tables (only when the group budget forces padding)
+    int ngroups;  // 32 KB each
+    int lg[kMaxGroups];    // log2(tables in the group)
+    int base[kMaxGroups];  // first slot of the group
+};
+// greedy decomposition of the smallest k' >= k that needs <= maxgroups groups of <= 2^maxlg tables
+__host__ __device__ constexpr TabLayout make_layout(int k, int maxlg, int maxgroups)
 {
-#ifdef GEC_FORCE_LG
-    return GEC_FORCE_LG;
-#endif
-    return k <= 6 ? 0 : (k <= 12 ? 1 : (k <= 24 ? 2 : 3));
+    for (int kp = k; kp <= 2 * kMaxK; kp++) {
+        TabLayout L{};
+        int rem = kp, pos = 0, ng = 0;
+        bool ok = true;
+        while (rem > 0) {
+            int lg = maxlg;
+            while ((1 << lg) > rem) lg--;
+            if (ng >= kMaxGroups || ng >= maxgroups) {
+                ok = false;
+                break;
+            }
+            L.lg[ng] = lg;
+            L.base[ng] = pos;
+            ng++;
+            pos += 1 << lg;
+            rem -= 1 << lg;
+        }
+        if (ok) {
+            L.nslots = kp;
+            L.ngroups = ng;
+            return L;
+        }
+    }
+    return TabLayout{};
 }
-__host__ __device__ constexpr int slots_for_k(int k)
+__host__ __device__ constexpr int slot_group(const TabLayout &L, int u)
 {
-    return ((k + (1 << log2_group_for_k(k)) - 1) >> log2_group_for_k(k)) << log2_group_for_k(k);
+    int g = 0;
+    for (int i = 0; i < L.ngroups; i++)
+        if (u >= L.base[i]) g = i;
+    return g;
 }
+
+// Per-stripe decode plan of one stripe as the streaming kernel needs it (two slots, one per
+// table buffer).
+struct PlanSlot {
+    unsigned long long key_present, key_out;
+    uint32_t sid;         // stripe index (>= n: no more work)
+    int32_t rows;         // rows to produce in this pass (<= 0: nothing to do)
+    uint32_t chunk_next;  // next unclaimed 32-column chunk of this stripe
+    uint32_t len;         // shard_len of the stripe
+    uint32_t src_off[kMaxK];             // byte offset of source j inside the stripe
+    uint32_t dst_off[kRowsPerPass];      // byte offset of output row i inside the stripe
+    uint8_t coef[kRowsPerPass * kMaxK];  // coef[i*kMaxK + j]
+};
+constexpr uint32_t kAuxBytes = 2 * sizeof(PlanSlot) + 8 * (4 + 32) + 64;  // plan slots + mbarriers
+
+// consumer warps.  LDG shapes from the round-1 sweeps (2 x S x 4 registers of column data per thread);
+// TMA: S x 4 registers of column data, capped by the stage memory.
+__host__ __device__ constexpr int cfg_nw_ldg(int k, int mode)
+{
+    if (mode == kModeVerify) return k <= 11 ? 32 : 16;
+    return k <= 4 ? 32 : (k <= 6 ? 24 : (k <= 8 ? 20 : 16));
+}
+// TMA: at most 3 table groups per buffer, fewer (= more zero-table padding) when the table buffers
+// would not leave room for the stages of at least 8 consumer warps
+__host__ __device__ constexpr int cfg_tma_groups(int k, int bufs, int stage_rows)
+{
+    for (int g = 3; g > 1; g--) {
+        const TabLayout L = make_layout(k, 5, g);
+        if ((uint32_t)bufs * L.ngroups * kGroupBytes + kAuxBytes + 8u * stage_rows * kStageRowBytes <= kSmemLimit) return g;
+    }
+    return 1;
+}
+__host__ __device__ constexpr int cfg_nw_tma(int regs_est, uint32_t tab_bytes, int stage_rows)
+{
+    // the register file is split over the 4 sub-partitions of an SM (16384 registers each), so the
+    // per-thread budget only changes with ceil(warps / 4): 8 warps 255, 12: 168, 16: 128, 20: 96, 24: 80
+    int nw = 8;
+    for (int cand = 24; cand > 8; cand -= 4) {
+        const int cap = 16384 / (cand / 4 * 32) / 8 * 8;
+        if (cap >= regs_est) {
+            nw = cand;
+            break;
+        }
+    }
+    while (nw > 4 && tab_bytes + kAuxBytes + (uint32_t)nw * stage_rows * kStageRowBytes > kSmemLimit) nw -= 4;
+    return nw;
+}
+
+// ---- launch shape / shared-memory carve-up per (K, MODE), all compile time ------------------
+template <int K, int MODE> struct StreamCfg {
+    static constexpr int kTmaOverride = MODE == kModeEncode ? GEC_TMA_ENC : (MODE == kModePlan ? GEC_TMA_PLAN : GEC_TMA_VER);
+    static constexpr bool kTma = K > 16 || (kTmaOverride >= 0 ? (kTmaOverride != 0) : (MODE == kModeVerify || K >= GEC_TMA_FROM_K));
+    static constexpr int kBufs = MODE == kModePlan ? 2 : 1;  // table buffers
+    static constexpr int kStageRows = kTma ? K + (MODE == kModeVerify ? kRowsPerPass : 0) : 0;
+    static constexpr int kNwOverride = MODE == kModeEncode ? GEC_NW_ENC : (MODE == kModePlan ? GEC_NW_PLAN : GEC_NW_VER);
+
+    // LDG: groups of <= 8 tables (>= 64 contiguous bytes per shard and warp instruction), tables
+    // <= 192 KB so that >= 32 KB stay L1 (round 1: 224 KB of tables starved the global loads).
+    // TMA: groups of <= 32 tables, <= 3 groups per buffer; the loads bypass L1.
+    static constexpr int kMaxLg = kTma ? 5 : 3;
+    static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows) : 6 / kBufs;
+    static constexpr TabLayout kLay = make_layout(K, kMaxLg, kMaxGrp);
+    static constexpr int S = kLay.nslots;
+    static constexpr uint32_t kTabBytes = (uint32_t)kBufs * kLay.ngroups * kGroupBytes;
+
+    // consumer warps: LDG shapes from the round-1 sweeps (2 x S x 4 registers of column data);
+    // TMA: S x 4 registers of column data, capped by the stage memory
+    static constexpr int kWarpsDefault = kTma ? cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows) : cfg_nw_ldg(K, MODE);
+    static constexpr int kWarpsAll = kNwOverride > 0 ? kNwOverride : kWarpsDefault;
+    // reconstruct: the last warp is the table builder
+    static constexpr int kWarps = MODE == kModePlan ? kWarpsAll - 1 : kWarpsAll;  // consumer warps
+    static constexpr int kThreads = 32 * kWarpsAll;
+    static constexpr uint32_t kStageBytes = (uint32_t)kWarps * kStageRows * kStageRowBytes;
+    static constexpr uint32_t kSmem = kTabBytes + kStageBytes + kAuxBytes;
+    static_assert(kLay.nslots >= K && kLay.ngroups >= 1, "no table layout for this k");
+    static_assert(kSmem <= kSmemLimit, "shared memory budget exceeded");
+    static_assert(kThreads <= 1024 && kWarps >= 1, "bad launch shape");
+};
 
 // GF(2^8) antilog / log tables, pinned in constant memory.  Kernels that need general products
 // (decode planning) stage them into shared memory with warp-UNIFORM 16-byte constant loads:
@@ -106,8 +227,6 @@ __device__ __forceinline__ void stage_gf_tables(uint8_t *s_gf /* 768 B, 16-byte 
             reinterpret_cast<uint32_t *>(s_gf)[i * 4 + lane] = lane == 0 ? v.x : (lane == 1 ? v.y : (lane == 2 ? v.z : v.w));
     }
 }
-
-enum ApplyMode { kModeEncode = 0, kModePlan = 1, kModeVerify = 2 };
 
 // Per-stripe decode plan, produced by rs_plan_kernel, consumed by rs_apply_kernel<kModePlan>.
 struct __align__(16) StripePlan {
@@ -141,6 +260,14 @@ struct ApplyParams {
 };
 
 // ------------------------------------------------------------------ small device helpers
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
 __device__ __forceinline__ uint4 ldg_stream(const void *p)
 {
     uint4 r;
@@ -161,6 +288,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
 // zero the bytes at positions >= nbytes (0 < nbytes < 16) of a 16-byte vector
 __device__ __forceinline__ uint4 mask_tail(uint4 v, uint32_t nbytes)
 {
@@ -172,6 +305,45 @@ __device__ __forceinline__ uint4 mask_tail(uint4 v, uint32_t nbytes)
         else if ((int)nbytes < lo + 4) w[i] &= 0xffffffffu >> (8 * (lo + 4 - (int)nbytes));
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA) ----------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "GEC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra GEC_DONE;\n"
+        "bra GEC_WAIT;\n"
+        "GEC_DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> this CTA's shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
 // 4x4 byte transpose: a[p] holds {row0,row1,row2,row3} bytes of byte column p;
@@ -190,38 +362,6 @@ __device__ __forceinline__ void transpose4x4(const uint32_t a0, const uint32_t a
     r3 = __byte_perm(t2, t3, 0x7632);
 }
 
-// ------------------------------------------------------------------ shared memory carve-up
-// Decode plan of one stripe as the streaming kernel needs it (two slots: current / next).
-struct PlanSlot {
-    unsigned long long key_present, key_out;
-    uint32_t sid;   // stripe index (>= n: no more work)
-    int32_t rows;   // rows to produce in this pass (<= 0: nothing to do)
-    uint32_t chunk_next;  // next unclaimed 32-column chunk of this stripe (warps claim them dynamically)
-    uint32_t pad;
-    uint32_t src_off[kMaxK];           // byte offset of source j inside the stripe
-    uint32_t dst_off[kRowsPerPass];    // byte offset of output row i inside the stripe
-    uint8_t coef[kRowsPerPass * kMaxK];  // coef[i*kMaxK + j]
-};
-struct SmemLayout {
-    // dynamic smem: [table groups: ceil(k/G) * 32 KB][PlanSlot x 2]
-    uint32_t *tab;
-    PlanSlot *slot;
-};
-constexpr size_t kSmemAux = 2 * sizeof(PlanSlot) + 16;
-__host__ __device__ inline size_t smem_bytes_for(int k)
-{
-    return (size_t)(slots_for_k(k) >> log2_group_for_k(k)) * kGroupBytes + kSmemAux;
-}
-
-__device__ __forceinline__ SmemLayout carve(unsigned char *base, uint32_t k)
-{
-    SmemLayout L;
-    L.tab = reinterpret_cast<uint32_t *>(base);
-    L.slot = reinterpret_cast<PlanSlot *>(
-        base + (size_t)(slots_for_k((int)k) >> log2_group_for_k((int)k)) * kGroupBytes);
-    return L;
-}
-
 // multiply four packed GF(2^8) bytes by alpha (= 2): shift left, reduce by 0x11D where bit 7 was set
 __device__ __forceinline__ uint32_t xtime4(uint32_t v)
 {
@@ -229,82 +369,85 @@ __device__ __forceinline__ uint32_t xtime4(uint32_t v)
     return ((v ^ hi) << 1) ^ ((hi >> 7) * 0x1du);
 }
 
-// Build the product tables for `rows` (<=4) coefficient rows coef[i*cstride + j], j < k; the
-// padding tables of a partial last group are all zero.  No log/antilog lookups: entry x of
-// table j is XOR_{bit b of x} (packed column j) * alpha^b, split as Hi[x >> 4] ^ Lo[x & 15].
-// Caller syncs before and after.
-//  * G <= 2 (k <= 14): warp-cooperative.  Each lane keeps Lo[lane & 15] / Hi[lane & 15] of its
-//    sub-warp's table in two registers; an entry is two shuffles + XOR; one STS.128 instruction
-//    of a warp writes 4 rows x (all replicas) = 512 B over all 32 banks in the minimum 4
-//    wavefronts (a row-per-lane mapping would serialise 32-way on the replica banks).
-//  * G >= 4: plain loop (generic path).
-template <int NT>
-__device__ __forceinline__ void build_tables(const SmemLayout &L, const uint8_t *coef, uint32_t cstride,
-                                             uint32_t k, uint32_t rows)
+// ------------------------------------------------------------------ product tables
+// Build the tables of `rows` (<= 4) coefficient rows coef[i*cstride + j], j < K, into one table
+// buffer; slots >= K are zero.  Entry x of table j is XOR_{bit b of x} (packed column j)*alpha^b.
+// Every lane owns one 16-byte bank quad (qd = lane & 7) of the rows x = 4*g + (lane >> 3): it
+// keeps the eight powers of its quad's table(s) in registers and walks g in Gray-code order, so
+// an entry costs ONE xor per table, and one STS.128 instruction of the warp writes 4 full rows
+// (512 B over all 32 banks, the minimum 4 wavefronts).  Work unit = (group, 8 Gray steps);
+// units are dealt round-robin to the `nw` participating warps (`w` = this warp's index).
+template <class LAYC>
+__device__ __forceinline__ void build_tables(uint32_t *tab, const uint8_t *coef, uint32_t cstride, uint32_t rows,
+                                             uint32_t w, uint32_t nw, int K)
 {
-    const uint32_t lg = (uint32_t)log2_group_for_k((int)k);
-    const uint32_t slots = (uint32_t)slots_for_k((int)k);
-    const uint32_t R = 32u >> lg;  // replicas per table = lanes per sub-warp (>= 4)
+    constexpr TabLayout LAY = LAYC::kLay;
+    const uint32_t lane = threadIdx.x & 31, qd = lane & 7, xs = lane >> 3;
     auto packed_col = [&](uint32_t j) -> uint32_t {
         uint32_t cur = 0;
-        if (j < k) {
+        if (j < (uint32_t)K) {
 #pragma unroll
             for (uint32_t i = 0; i < kRowsPerPass; i++)
                 if (i < rows) cur |= (uint32_t)coef[i * cstride + j] << (8 * i);
         }
         return cur;
     };
-    if (lg <= 1) {
-        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const uint32_t sub = lg ? (lane >> 4) : 0;           // table of the group this lane writes
-        const uint32_t quads = R >> 2;                        // 16-byte pieces per row and table
-        const uint32_t quad = lane & (quads - 1);
-        const uint32_t xsel = (lane >> (lg ? 2 : 3)) & 3;     // which of the 4 rows of this instruction
-        const uint32_t total = (slots >> lg) * 64;            // STS.128 warp-instructions
-        const uint32_t per = (total + NT / 32 - 1) / (NT / 32);
-        const uint32_t i0 = warp * per, i1 = min(total, i0 + per);
-        uint32_t tprev = 0xffffffffu, lo = 0, hi = 0;
-        for (uint32_t I = i0; I < i1; I++) {
-            const uint32_t t = I >> 6, r4 = I & 63;
-            if (t != tprev) {
-                uint32_t cur = packed_col((t << lg) + sub);
-                const uint32_t idx = lane & 15;
-                lo = 0;
-                hi = 0;
+    static_for<0, LAY.ngroups>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        constexpr int lg = LAY.lg[g];
+        constexpr int NTQ = lg <= 3 ? 1 : (lg == 4 ? 2 : 4);  // tables inside one bank quad
+        // does this warp own a unit of this group at all?
+        bool any = false;
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if ((idx >> b) & 1) lo ^= cur;
-                    cur = xtime4(cur);
-                }
+        for (int sg = 0; sg < 8; sg++) any |= ((uint32_t)(g * 8 + sg) % nw) == w;
+        if (!any) return;
+        uint32_t pw[NTQ][8];
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if ((idx >> b) & 1) hi ^= cur;
-                    cur = xtime4(cur);
-                }
-                tprev = t;
+        for (int t = 0; t < NTQ; t++) {
+            // banks 4*qd + (4/NTQ)*t ... belong to table (bank >> (5 - lg)) of the group
+            const uint32_t bank = 4 * qd + (4 / NTQ) * t;
+            uint32_t cur = packed_col(LAY.base[g] + (bank >> (5 - lg)));
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                pw[t][b] = cur;
+                cur = xtime4(cur);
             }
-            const uint32_t x = r4 * 4 + xsel;
-            const uint32_t w = __shfl_sync(0xffffffffu, lo, (lane & 16) + (x & 15)) ^
-                               __shfl_sync(0xffffffffu, hi, (lane & 16) + (x >> 4));
-            uint32_t *dst = L.tab + (size_t)t * (kGroupBytes / 4) + x * 32 + sub * R + quad * 4;
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(w, w, w, w);
         }
-        return;
-    }
-    for (uint32_t e = threadIdx.x; e < slots * 256; e += NT) {
-        const uint32_t j = e >> 8, x = e & 255;
-        uint32_t w = 0;
-        uint32_t cur = packed_col(j);
+#pragma unroll 1
+        for (uint32_t sg = 0; sg < 8; sg++) {
+            if (((uint32_t)(g * 8) + sg) % nw != w) continue;
+            const uint32_t n0 = sg * 8;
+            uint32_t gx = n0 ^ (n0 >> 1);  // Gray code of the first step of the segment
+            uint32_t e[NTQ];
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            if ((x >> b) & 1) w ^= cur;
-            cur = xtime4(cur);
+            for (int t = 0; t < NTQ; t++) {
+                uint32_t v = 0;
+                if (xs & 1) v ^= pw[t][0];
+                if (xs & 2) v ^= pw[t][1];
+#pragma unroll
+                for (int b = 0; b < 6; b++)
+                    if ((gx >> b) & 1) v ^= pw[t][2 + b];
+                e[t] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t x = gx * 4 + xs;
+                uint4 v;
+                if (NTQ == 1) v = make_uint4(e[0], e[0], e[0], e[0]);
+                else if (NTQ == 2) v = make_uint4(e[0], e[0], e[NTQ - 1], e[NTQ - 1]);
+                else v = make_uint4(e[0], e[1 % NTQ], e[2 % NTQ], e[3 % NTQ]);
+                *reinterpret_cast<uint4 *>(tab + (size_t)g * (kGroupBytes / 4) + x * 32 + qd * 4) = v;
+                if (i < 7) {
+                    // Gray step n -> n+1 flips bit ctz(n+1); inside an aligned segment of 8 it only
+                    // depends on i
+                    const int c = (i & 1) == 0 ? 0 : ((i & 3) == 1 ? 1 : 2);
+                    gx ^= 1u << c;
+#pragma unroll
+                    for (int t = 0; t < NTQ; t++) e[t] ^= pw[t][2 + c];
+                }
+            }
         }
-        // table j: group t = j >> lg, banks [sub*R, sub*R + R), row x
-        uint32_t *dst = L.tab + (size_t)(j >> lg) * (kGroupBytes / 4) + x * 32 + (j & ((1u << lg) - 1)) * R;
-        const uint4 v = make_uint4(w, w, w, w);
-        for (uint32_t g = 0; g < R; g += 4) *reinterpret_cast<uint4 *>(dst + g) = v;
-    }
+    });
 }
 
 // 16 table lookups for one 16-byte vector; acc[4*w + p] ^= T[byte p of word w]
@@ -337,122 +480,120 @@ __device__ __forceinline__ void rows_from_acc(const uint32_t (&acc)[16], uint4 (
     for (int row = 0; row < 4; row++) r[row] = make_uint4(o[row][0], o[row][1], o[row][2], o[row][3]);
 }
 
-// One 16-byte column of one stripe.  Slot u of a lane in sub-warp q holds source u ^ q (see file
-// header); slots >= k (padding of a partial last group) hold zeros.
-//   sp     : address of this column in source 0 (uniform modes) / shard 0 (plan mode)
-//   kPlan  : source j lives at sp + src_off[j] (smem) instead of sp + j*stride
-template <int K, bool kPlan>
-__device__ __forceinline__ void column_load(const uint8_t *sp, uint32_t stride, const uint32_t *src_off,
-                                            uint32_t q, uint4 (&d)[slots_for_k(K)])
+// Source shard read by this lane in slot u: slot u = phase p of group g; sub-warp q = lane / R
+// of the group works on source base + (p xor q).
+template <class CFG, int U> __device__ __forceinline__ uint32_t lane_source(uint32_t lane)
 {
-    constexpr int S = slots_for_k(K);
-#pragma unroll
-    for (int u = 0; u < S; u++) {
-        const uint32_t j = (uint32_t)u ^ q;
-        if (S == K || j < (uint32_t)K) d[u] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
+    constexpr TabLayout LAY = CFG::kLay;
+    constexpr int g = slot_group(LAY, U);
+    constexpr int lg = LAY.lg[g];
+    constexpr int ph = U - LAY.base[g];
+    return (uint32_t)LAY.base[g] + ((uint32_t)ph ^ (lg ? (lane >> (5 - lg)) : 0u));
+}
+template <class CFG, int U> __device__ __forceinline__ constexpr bool slot_may_pad()
+{
+    constexpr TabLayout LAY = CFG::kLay;
+    constexpr int g = slot_group(LAY, U);
+    return LAY.base[g] + (1 << LAY.lg[g]) > (int)CFG::kK;
+}
+
+// LDG: one 16-byte column of every source straight into registers.
+//   sp     : address of this lane's column in source 0 (uniform modes) / shard 0 (plan mode)
+//   kPlan  : source j lives at sp + src_off[j] (smem) instead of sp + j*stride
+template <class CFG, bool kPlan>
+__device__ __forceinline__ void column_load(const uint8_t *sp, uint32_t stride, const uint32_t *src_off,
+                                            uint32_t lane, uint4 (&d)[CFG::S])
+{
+    static_for<0, CFG::S>([&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        const uint32_t j = lane_source<CFG, u>(lane);
+        if (!slot_may_pad<CFG, u>() || j < (uint32_t)CFG::kK) d[u] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
         else d[u] = make_uint4(0, 0, 0, 0);
-    }
+    });
+}
+// TMA: the same vectors out of the warp's stage (row j = source j, 512 B per row)
+template <class CFG>
+__device__ __forceinline__ void stage_read(uint32_t stage_lane_addr /* stage + lane*16 */, uint32_t lane,
+                                           uint4 (&d)[CFG::S])
+{
+    static_for<0, CFG::S>([&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        const uint32_t j = lane_source<CFG, u>(lane);
+        if (!slot_may_pad<CFG, u>() || j < (uint32_t)CFG::kK) d[u] = lds_v4(stage_lane_addr + j * kStageRowBytes);
+        else d[u] = make_uint4(0, 0, 0, 0);
+    });
 }
 
 // look up + transpose -> r[row] (uint4) for the slots of one column
-//   tab_base : shared address of the tables
-template <int K>
-__device__ __forceinline__ void column_compute(uint4 (&d)[slots_for_k(K)], uint32_t tab_base, uint32_t lane,
+//   tab_addr : shared address of the table buffer
+template <class CFG>
+__device__ __forceinline__ void column_compute(uint4 (&d)[CFG::S], uint32_t tab_addr, uint32_t lane,
                                                uint32_t row_bytes, uint32_t tail_bytes, uint4 (&r)[4])
 {
-    constexpr int S = slots_for_k(K);
-    constexpr int LG = log2_group_for_k(K);
-    constexpr uint32_t R = 32u >> LG;
+    constexpr TabLayout LAY = CFG::kLay;
     uint32_t acc[16];
     if (tail_bytes) {
 #pragma unroll
-        for (int u = 0; u < S; u++) d[u] = mask_tail(d[u], tail_bytes);
+        for (int u = 0; u < CFG::S; u++) d[u] = mask_tail(d[u], tail_bytes);
     }
-#pragma unroll
-    for (int u = 0; u < S; u++) {
-        // group u >> LG, phase u & (G-1): this lane's bank is lane ^ (phase * R)
-        const uint32_t base = tab_base + ((lane ^ (((uint32_t)u & ((1u << LG) - 1)) * R)) << 2) +
-                              (uint32_t)(u >> LG) * kGroupBytes;
-        if (u == 0) lookup16<true>(acc, d[u], base, row_bytes);
-        else lookup16<false>(acc, d[u], base, row_bytes);
-    }
-    rows_from_acc(acc, r);
-}
-
-// generic k (runtime, k > 16): batches of 8 slots, the next batch prefetched while one is looked up
-template <bool kPlan>
-__device__ __forceinline__ void column_rows_generic(const uint8_t *sp, uint32_t stride, uint32_t k_rt,
-                                                    const uint32_t *src_off, uint32_t tab_base,
-                                                    uint32_t row_bytes, uint32_t tail_bytes, uint32_t lane,
-                                                    uint4 (&r)[4])
-{
-    const uint32_t lg = (uint32_t)log2_group_for_k((int)k_rt);
-    const uint32_t G = 1u << lg, R = 32u >> lg;
-    const uint32_t q = lane >> (5 - lg);
-    const uint32_t slots = (uint32_t)slots_for_k((int)k_rt);
-    uint32_t acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = 0;
-    constexpr int W = 8;  // slots per batch; the next batch is in flight while this one is looked up
-    auto load_batch = [&](uint32_t u0, uint4 (&d)[W]) {
-#pragma unroll
-        for (int v = 0; v < W; v++) {
-            const uint32_t j = (u0 + v) ^ q;
-            d[v] = make_uint4(0, 0, 0, 0);
-            if (u0 + v < slots && j < k_rt) {
-                d[v] = ldg_stream(sp + (kPlan ? src_off[j] : j * stride));
-                if (tail_bytes) d[v] = mask_tail(d[v], tail_bytes);
-            }
-        }
-    };
-    uint4 dn[W];
-    load_batch(0, dn);
-    for (uint32_t u0 = 0; u0 < slots; u0 += W) {
-        uint4 d[W];
-#pragma unroll
-        for (int v = 0; v < W; v++) d[v] = dn[v];
-        if (u0 + W < slots) load_batch(u0 + W, dn);
-#pragma unroll
-        for (int v = 0; v < W; v++) {
-            const uint32_t u = u0 + v;
-            if (u < slots) {
-                const uint32_t base = tab_base + ((lane ^ ((u & (G - 1)) * R)) << 2) + (u >> lg) * kGroupBytes;
-                lookup16<false>(acc, d[v], base, row_bytes);
-            }
-        }
-    }
+    static_for<0, CFG::S>([&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        constexpr int g = slot_group(LAY, u);
+        constexpr int lg = LAY.lg[g];
+        constexpr int ph = u - LAY.base[g];
+        // this lane's bank at phase ph of group g: lane xor ph*R
+        const uint32_t base = tab_addr + (uint32_t)g * kGroupBytes + ((lane ^ ((uint32_t)ph << (lg ? 5 - lg : 0))) << 2);
+        lookup16<u == 0>(acc, d[u], base, row_bytes);
+    });
     rows_from_acc(acc, r);
 }
 
 // ------------------------------------------------------------------ the streaming kernel
-template <int K, int MODE, int NT, bool PIPE>
-__global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __grid_constant__ ApplyParams p)
+template <int K, int MODE> struct KernelCfg : StreamCfg<K, MODE> {
+    static constexpr int kK = K;
+};
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kernel(const __grid_constant__ ApplyParams p)
 {
-    constexpr int kThreads = NT;
+    using CFG = KernelCfg<K, MODE>;
+    constexpr int S = CFG::S;
+    constexpr int NW = CFG::kWarps;  // consumer warps
+    constexpr bool TMA = CFG::kTma;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const SmemLayout L = carve(smem_raw, p.k);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t k = (K > 0) ? (uint32_t)K : p.k;
-    constexpr int KD = K > 0 ? K : 1;
-    constexpr int SD = slots_for_k(KD);
+    uint32_t *const tab = reinterpret_cast<uint32_t *>(smem_raw);
+    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t stage_addr = tab_addr + CFG::kTabBytes + warp * (CFG::kStageRows * kStageRowBytes);
+    PlanSlot *const slot = reinterpret_cast<PlanSlot *>(smem_raw + CFG::kTabBytes + CFG::kStageBytes);
+    const uint32_t bars = tab_addr + CFG::kTabBytes + CFG::kStageBytes + 2 * (uint32_t)sizeof(PlanSlot);
+    const uint32_t bar_full = bars, bar_empty = bars + 16, bar_stage = bars + 32 + warp * 8;  // full[2], empty[2], stage[NW]
 
-    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(L.tab);
-    const uint32_t q = lane >> (5 - log2_group_for_k((int)k));  // sub-warp index
+    if (tid == 0) {
+        mbar_init(bar_full, 32);
+        mbar_init(bar_full + 8, 32);
+        mbar_init(bar_empty, NW);
+        mbar_init(bar_empty + 8, NW);
+    }
+    if (TMA && lane == 0 && warp < (uint32_t)NW) mbar_init(bar_stage, 1);
+    mbar_fence_init();
+    uint32_t stage_parity = 0;
 
-    if (MODE != kModePlan) {
+    // TMA: lane 0 arms the warp's stage with `nrow` x `rb` bytes; the copies are issued by the caller
+    if constexpr (MODE != kModePlan) {
         // ---- uniform coefficient matrix: build once, then warps stream items ----------------
-        build_tables<NT>(L, p.coef, k, k, p.rows);
+        build_tables<CFG>(tab, p.coef, K, p.rows, warp, (uint32_t)NW, K);
         __syncthreads();
 
         const uint32_t ips = p.items_per_stripe;
         const uint32_t total = p.n * ips;  // host guarantees < 2^32
-        const uint32_t gwarps = gridDim.x * (kThreads / 32);
+        const uint32_t gwarps = gridDim.x * NW;
 
         // position of this lane's column for a work item (stripe, 32-column chunk)
         struct Pos {
-            const uint8_t *sp;
-            uint32_t s, col, tail;
-            bool valid;
+            const uint8_t *sp;  // this lane's column in source 0
+            uint32_t s, col, tail, rb;
+            bool valid, any;  // this lane has a column / the warp has at least one
         };
         auto locate = [&](uint32_t item) -> Pos {
             Pos z;
@@ -462,11 +603,26 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
             const uint32_t nvec = (len + 15) >> 4;
             z.col = c * 32 + lane;
             z.valid = z.col < nvec;
+            z.any = c * 32 < nvec;
             z.tail = (z.col == nvec - 1) ? (len & 15) : 0;
+            z.rb = z.any ? min(kStageRowBytes, (nvec - c * 32) * 16) : 0;
             z.sp = p.src + (unsigned long long)z.s * p.src_pitch + (size_t)z.col * 16;
             return z;
         };
-        auto finish = [&](const Pos &z, const uint4 (&r)[4]) {
+        // TMA: arm the stage and issue one bulk copy per staged row (lane 0)
+        auto issue = [&](const Pos &z) {
+            if (!z.any || lane != 0) return;  // lane 0's column is the first of the chunk
+            constexpr int NR = CFG::kStageRows;
+            const uint32_t nrow = MODE == kModeVerify ? (uint32_t)K + p.rows : (uint32_t)K;
+            mbar_arrive_expect_tx(bar_stage, z.rb * nrow);
+#pragma unroll
+            for (int j = 0; j < NR; j++) {
+                if (j < K) bulk_g2s(stage_addr + j * kStageRowBytes, z.sp + (size_t)j * p.stride, z.rb, bar_stage);
+                else if ((uint32_t)(j - K) < p.rows)
+                    bulk_g2s(stage_addr + j * kStageRowBytes, z.sp + (size_t)(j + p.row_off) * p.stride, z.rb, bar_stage);
+            }
+        };
+        auto finish = [&](const Pos &z, const uint4 (&r)[4], const uint4 (&st)[4]) {
             uint32_t mm = 0;
             if (MODE == kModeEncode) {
                 if (z.valid) {
@@ -477,15 +633,12 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
                 }
             } else {
                 if (z.valid) {
-                    // stored parity rows follow the k data shards of the same stripe
-                    const uint8_t *pp = z.sp + (size_t)(k + p.row_off) * p.stride;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         if (i < (int)p.rows) {
-                            uint4 st = ldg_stream(pp + (size_t)i * p.stride);
-                            if (z.tail) st = mask_tail(st, z.tail);
-                            const uint32_t diff = (st.x ^ r[i].x) | (st.y ^ r[i].y) | (st.z ^ r[i].z) |
-                                                  (st.w ^ r[i].w);
+                            uint4 sv = st[i];
+                            if (z.tail) sv = mask_tail(sv, z.tail);
+                            const uint32_t diff = (sv.x ^ r[i].x) | (sv.y ^ r[i].y) | (sv.z ^ r[i].z) | (sv.w ^ r[i].w);
                             if (diff) mm |= 1u << (p.row_off + i);
                         }
                     }
@@ -495,180 +648,244 @@ __global__ void __launch_bounds__(NT, GEC_MIN_BLOCKS) rs_apply_kernel(const __gr
                 if (mm && lane == 0) atomicOr(p.mismatch + z.s, mm);
             }
         };
+        // stored parity rows of a verify item (they follow the k data shards of the same stripe)
+        auto load_stored = [&](const Pos &z, uint4 (&st)[4]) {
+            if (MODE != kModeVerify) return;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                st[i] = make_uint4(0, 0, 0, 0);
+                if (i < (int)p.rows && z.valid) {
+                    if (TMA) st[i] = lds_v4(stage_addr + lane * 16 + (K + i) * kStageRowBytes);
+                    else st[i] = ldg_stream(z.sp + (size_t)(K + p.row_off + i) * p.stride);
+                }
+            }
+        };
 
-        uint32_t item = blockIdx.x * (kThreads / 32) + warp;
-        if (K > 0 && PIPE) {
-            uint4 dn[SD];
+        uint32_t item = blockIdx.x * NW + warp;
+        if constexpr (TMA) {
             Pos nx;
-            nx.valid = false;
+            nx.valid = nx.any = false;
             if (item < total) {
                 nx = locate(item);
-                if (nx.valid) column_load<KD, false>(nx.sp, p.stride, nullptr, q, dn);
+                issue(nx);
             }
             while (item < total) {
-                uint4 d[SD];
-#pragma unroll
-                for (int u = 0; u < SD; u++) d[u] = dn[u];
                 const Pos cur = nx;
+                uint4 d[S], st[4];
+                if (cur.any) {
+                    mbar_wait(bar_stage, stage_parity);
+                    stage_parity ^= 1;
+                    stage_read<CFG>(stage_addr + lane * 16, lane, d);
+                    load_stored(cur, st);
+                }
+                __syncwarp();  // every lane has its vectors: the stage may be refilled
                 item += gwarps;
-                nx.valid = false;
+                nx.valid = nx.any = false;
                 if (item < total) {
                     nx = locate(item);
-                    if (nx.valid) column_load<KD, false>(nx.sp, p.stride, nullptr, q, dn);
+                    issue(nx);
                 }
                 uint4 r[4];
-                if (cur.valid) column_compute<KD>(d, tab_base, lane, p.row_bytes, cur.tail, r);
-                finish(cur, r);
+                if (cur.valid) column_compute<CFG>(d, tab_addr, lane, p.row_bytes, cur.tail, r);
+                finish(cur, r, st);
             }
         } else {
-            for (; item < total; item += gwarps) {
-                const Pos cur = locate(item);
-                uint4 r[4];
-                if (cur.valid) {
-                    if (K > 0) {
-                        uint4 d[SD];
-                        column_load<KD, false>(cur.sp, p.stride, nullptr, q, d);
-                        column_compute<KD>(d, tab_base, lane, p.row_bytes, cur.tail, r);
-                    } else {
-                        column_rows_generic<false>(cur.sp, p.stride, k, nullptr, tab_base, p.row_bytes,
-                                                   cur.tail, lane, r);
-                    }
+            uint4 dn[S], stn[4];
+            Pos nx;
+            nx.valid = nx.any = false;
+            if (item < total) {
+                nx = locate(item);
+                if (nx.valid) column_load<CFG, false>(nx.sp, p.stride, nullptr, lane, dn);
+                load_stored(nx, stn);
+            }
+            while (item < total) {
+                uint4 d[S], st[4];
+#pragma unroll
+                for (int u = 0; u < S; u++) d[u] = dn[u];
+#pragma unroll
+                for (int i = 0; i < 4; i++) st[i] = stn[i];
+                const Pos cur = nx;
+                item += gwarps;
+                nx.valid = nx.any = false;
+                if (item < total) {
+                    nx = locate(item);
+                    if (nx.valid) column_load<CFG, false>(nx.sp, p.stride, nullptr, lane, dn);
+                    load_stored(nx, stn);
                 }
-                finish(cur, r);
+                uint4 r[4];
+                if (cur.valid) column_compute<CFG>(d, tab_addr, lane, p.row_bytes, cur.tail, r);
+                finish(cur, r, st);
             }
         }
     } else {
-        // ---- per-stripe matrices: CTAs pull stripes from an atomic counter -------------------
-        // Two plan slots: while the CTA streams stripe `cur`, warp 0 claims the next stripe and
-        // stages its plan; at the stripe boundary the first column loads of the new stripe are
-        // issued BEFORE its tables are rebuilt, so HBM latency hides behind the rebuild.
-        // Stripes are claimed one staging ahead: the atomic issued now is consumed by the NEXT call,
-        // so its round trip never sits between the CTA and the barrier that waits for the plan.
-        uint32_t claimed = 0;                  // meaningful in lane 0 of warp 0
-        auto stage_plan = [&](PlanSlot &ps) {  // executed by warp 0 only
-            const uint32_t s = __shfl_sync(0xffffffffu, claimed, 0);
+        // ---- per-stripe matrices, no block-wide barrier after this one --------------------------
+        __syncthreads();  // mbarriers initialised
+        constexpr uint32_t kTabBuf = CFG::kTabBytes / 2;
+        if (warp == (uint32_t)NW) {
+            // ===== builder warp: claim stripes, stage their plans, build their tables one stripe
+            // ahead of the consumers.  Stripe sequence number i uses buffer / slot i & 1.
+            uint32_t claimed = 0;
             if (lane == 0) claimed = atomicAdd(p.counter, 1u);
-            int rows = 0;
-            if (s < p.n) {
-                const StripePlan *pl = p.plan + s;
-                rows = pl->unrecoverable ? 0 : min(kRowsPerPass, (int)pl->nrows - (int)p.row_off);
-                if (rows > 0) {
-                    if (lane < k) ps.src_off[lane] = (uint32_t)pl->surv[lane] * p.stride;
-                    if (lane < (uint32_t)rows) ps.dst_off[lane] = (uint32_t)pl->out_idx[p.row_off + lane] * p.stride;
-                    for (uint32_t e = lane; e < (uint32_t)rows * kMaxK; e += 32)
-                        ps.coef[e] = pl->coef[p.row_off + e / kMaxK][e % kMaxK];
-                    if (lane == 0) {
-                        ps.key_present = pl->key_present;
-                        ps.key_out = pl->key_out;
+            // pattern whose tables each buffer holds (scalars, not arrays: `b` is a run-time index)
+            unsigned long long bp0 = ~0ull, bp1 = ~0ull, bo0 = ~0ull, bo1 = ~0ull;
+            bool have0 = false, have1 = false;
+            for (uint32_t i = 0;; i++) {
+                const uint32_t b = i & 1, use = i >> 1;
+                // every consumer warp has left the stripe that used this buffer and slot
+                if (use >= 1) mbar_wait(bar_empty + 8 * b, (use - 1) & 1);
+                PlanSlot &ps = slot[b];
+                const uint32_t s = __shfl_sync(0xffffffffu, claimed, 0);
+                if (lane == 0) claimed = atomicAdd(p.counter, 1u);  // consumed by the next iteration
+                int rows = 0;
+                unsigned long long kp = 0, ko = 0;
+                if (s < p.n) {
+                    const StripePlan *pl = p.plan + s;
+                    rows = pl->unrecoverable ? 0 : min(kRowsPerPass, (int)pl->nrows - (int)p.row_off);
+                    if (rows > 0) {
+                        if (lane < (uint32_t)K) ps.src_off[lane] = (uint32_t)pl->surv[lane] * p.stride;
+                        if (lane < (uint32_t)rows) ps.dst_off[lane] = (uint32_t)pl->out_idx[p.row_off + lane] * p.stride;
+                        for (uint32_t e = lane; e < (uint32_t)rows * kMaxK; e += 32)
+                            ps.coef[e] = pl->coef[p.row_off + e / kMaxK][e % kMaxK];
+                        kp = pl->key_present;
+                        ko = pl->key_out;
                     }
                 }
+                if (lane == 0) {
+                    ps.sid = s;
+                    ps.rows = rows;
+                    ps.chunk_next = 0;
+                    ps.len = s < p.n ? (p.shard_len ? __ldg(p.shard_len + s) : p.stride) : 0;
+                }
+                __syncwarp();
+                const bool same = b ? (have1 && kp == bp1 && ko == bo1) : (have0 && kp == bp0 && ko == bo0);
+                if (rows > 0 && !same) {
+                    build_tables<CFG>(tab + b * (kTabBuf / 4), ps.coef, kMaxK, (uint32_t)rows, 0, 1, K);
+                    if (b) {
+                        bp1 = kp;
+                        bo1 = ko;
+                        have1 = true;
+                    } else {
+                        bp0 = kp;
+                        bo0 = ko;
+                        have0 = true;
+                    }
+                }
+                mbar_arrive(bar_full + 8 * b);  // all 32 lanes: each lane's table stores are released by its own arrive
+                if (s >= p.n) break;
             }
-            if (lane == 0) {
-                ps.sid = s;
-                ps.rows = rows;
-                ps.chunk_next = kThreads / 32;  // chunk w < #warps belongs to warp w, the rest are claimed
+            return;
+        }
+
+        // ===== consumer warps
+        constexpr uint32_t kNone = 0xffffffffu;
+        uint32_t pos = 0;      // stripe sequence number the search is at
+        bool entered = false;  // full[pos] has been waited for
+        bool ended = false;    // the terminal slot (sid >= n) was seen
+        uint32_t pend = kNone; // sequence number of the item whose lookups are still to run
+        struct It {
+            uint32_t seq, s, chunk, nvec, len;
+            int rows;
+            bool valid;
+        };
+        auto leave = [&](uint32_t i) {  // this warp will not touch tables / slot of sequence i again
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * (i & 1));
+        };
+        // next work item of this warp; never waits for full[j] with j > lim (the builder may need
+        // this warp's `leave` of an older stripe first)
+        auto find = [&](uint32_t lim, It &it) {
+            it.valid = false;
+            while (!ended) {
+                if (!entered) {
+                    if (pos > lim) return;
+                    mbar_wait(bar_full + 8 * (pos & 1), (pos >> 1) & 1);
+                    entered = true;
+                }
+                PlanSlot &ps = slot[pos & 1];
+                const uint32_t s = ps.sid;
+                if (s >= p.n) {
+                    ended = true;
+                    return;
+                }
+                const int rows = ps.rows;
+                if (rows > 0) {
+                    const uint32_t len = ps.len, nvec = (len + 15) >> 4;
+                    uint32_t c = 0;
+                    if (lane == 0) c = atomicAdd(&ps.chunk_next, 1u);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c * 32 < nvec) {
+                        it.seq = pos;
+                        it.s = s;
+                        it.chunk = c;
+                        it.nvec = nvec;
+                        it.len = len;
+                        it.rows = rows;
+                        it.valid = true;
+                        return;
+                    }
+                }
+                if (pos != pend) leave(pos);  // else: deferred until the pending lookups are done
+                pos++;
+                entered = false;
             }
         };
-        if (warp == 0) {
-            if (lane == 0) claimed = atomicAdd(p.counter, 1u);
-            stage_plan(L.slot[0]);
-        }
-        __syncthreads();
-        unsigned long long built_present = ~0ull, built_out = ~0ull;
-        bool have_tables = false;
-        bool have_dn = false;  // dn already holds this thread's first column of the stripe in slot cs
-        uint4 dn[SD];
-        for (uint32_t cs = 0;; cs ^= 1) {
-            const PlanSlot &ps = L.slot[cs];
-            const uint32_t s = ps.sid;
-            if (s >= p.n) break;
-            const int rows = ps.rows;
-            uint32_t len = 0, nvec = 0;
-            const uint8_t *sbase = p.src + (unsigned long long)s * p.src_pitch;
-            uint8_t *dbase = p.dst + (unsigned long long)s * p.dst_pitch;
-            uint32_t col = tid;
-            if (rows > 0) {
-                len = p.shard_len ? __ldg(p.shard_len + s) : p.stride;
-                nvec = (len + 15) >> 4;
-                if (K > 0 && PIPE && col < nvec && !have_dn)
-                    column_load<KD, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, q, dn);
+        // start bringing in the columns of an item: TMA copies into the stage / LDG into dn
+        uint4 dn[TMA ? 1 : S];
+        auto fetch = [&](const It &it) {
+            const PlanSlot &ps = slot[it.seq & 1];
+            const uint8_t *sbase = p.src + (unsigned long long)it.s * p.src_pitch;
+            if constexpr (TMA) {
+                if (lane == 0) {
+                    const uint32_t rb = min(kStageRowBytes, (it.nvec - it.chunk * 32) * 16);
+                    mbar_arrive_expect_tx(bar_stage, rb * K);
+#pragma unroll
+                    for (int j = 0; j < K; j++)
+                        bulk_g2s(stage_addr + j * kStageRowBytes, sbase + ps.src_off[j] + (size_t)it.chunk * kStageRowBytes, rb,
+                                 bar_stage);
+                }
+            } else {
+                const uint32_t col = it.chunk * 32 + lane;
+                if (col < it.nvec) column_load<CFG, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, lane, dn);
             }
-            have_dn = false;
-            if (warp == 0) stage_plan(L.slot[cs ^ 1]);
-            if (rows > 0 && !(have_tables && ps.key_present == built_present && ps.key_out == built_out)) {
-                build_tables<NT>(L, ps.coef, kMaxK, k, (uint32_t)rows);
-                built_present = ps.key_present;
-                built_out = ps.key_out;
-                have_tables = true;
+        };
+
+        It nx;
+        find(kNone, nx);
+        if (nx.valid) fetch(nx);
+        while (nx.valid) {
+            const It cur = nx;
+            uint4 d[S];
+            if constexpr (TMA) {
+                mbar_wait(bar_stage, stage_parity);
+                stage_parity ^= 1;
+                stage_read<CFG>(stage_addr + lane * 16, lane, d);
+                __syncwarp();  // every lane has its vectors: the stage may be refilled
+            } else {
+#pragma unroll
+                for (int u = 0; u < S; u++) d[u] = dn[u];
             }
-            __syncthreads();  // tables of `s` complete, next plan staged
-            if (rows > 0) {
-                if (K > 0 && PIPE) {
-                    // 32-column chunks: chunk `warp` is this warp's first one, the rest are claimed
-                    // from a shared counter one iteration ahead, so every warp reaches the barrier
-                    // within one chunk of the others (a static col = tid + i*NT split lets the slow
-                    // warps' lag accumulate over the ~13 iterations of a stripe)
-                    // claims run one iteration ahead of their use, so the shared-memory atomic
-                    // never delays the prefetch loads.  Measured (profiles/r01_summary.md): RS(10,4)
-                    // with 4 erasures 0.905 -> 0.926, RS(6,3) 0.867 -> 0.905, RS(4,2) 0.949 -> 0.976;
-                    // a single erasure per stripe is slower than with the static split (0.91 -> 0.86).
-                    uint32_t chunk = warp, nxt = 0, nxt2 = 0;
-                    if (lane == 0) nxt = atomicAdd(&L.slot[cs].chunk_next, 1u);
-                    nxt = __shfl_sync(0xffffffffu, nxt, 0);
-                    while (chunk * 32 < nvec) {
-                        uint4 d[SD];
+            pend = cur.seq;
+            find(cur.seq + 1, nx);
+            if (nx.valid) fetch(nx);
+            {
+                const PlanSlot &ps = slot[cur.seq & 1];
+                const uint32_t col = cur.chunk * 32 + lane;
+                if (col < cur.nvec) {
+                    const uint32_t tail = (col == cur.nvec - 1) ? (cur.len & 15) : 0;
+                    uint4 r[4];
+                    column_compute<CFG>(d, tab_addr + (cur.seq & 1) * kTabBuf, lane, p.row_bytes, tail, r);
+                    uint8_t *dbase = p.dst + (unsigned long long)cur.s * p.dst_pitch;
 #pragma unroll
-                        for (int u = 0; u < SD; u++) d[u] = dn[u];
-                        const uint32_t cur = chunk * 32 + lane;
-                        if (lane == 0) nxt2 = atomicAdd(&L.slot[cs].chunk_next, 1u);  // consumed next iteration
-                        if (nxt * 32 < nvec) {
-                            const uint32_t ncol = nxt * 32 + lane;
-                            if (ncol < nvec)
-                                column_load<KD, true>(sbase + (size_t)ncol * 16, p.stride, ps.src_off, q, dn);
-                        } else {
-                            // no chunk left in this stripe for this warp: start on the next stripe
-                            // (its plan was staged before the barrier above) so HBM never drains
-                            const PlanSlot &nx = L.slot[cs ^ 1];
-                            if (nx.sid < p.n && nx.rows > 0) {
-                                const uint32_t nlen = p.shard_len ? __ldg(p.shard_len + nx.sid) : p.stride;
-                                if (tid < ((nlen + 15) >> 4)) {
-                                    column_load<KD, true>(p.src + (unsigned long long)nx.sid * p.src_pitch +
-                                                              (size_t)tid * 16,
-                                                          p.stride, nx.src_off, q, dn);
-                                    have_dn = true;
-                                }
-                            }
-                        }
-                        if (cur < nvec) {
-                            const uint32_t tail = (cur == nvec - 1) ? (len & 15) : 0;
-                            uint4 r[4];
-                            column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
-#pragma unroll
-                            for (int i = 0; i < 4; i++)
-                                if (i < rows) stg_stream(dbase + ps.dst_off[i] + (size_t)cur * 16, r[i]);
-                        }
-                        chunk = nxt;
-                        nxt = __shfl_sync(0xffffffffu, nxt2, 0);
-                    }
-                } else {
-                    for (; col < nvec; col += kThreads) {
-                        const uint32_t tail = (col == nvec - 1) ? (len & 15) : 0;
-                        uint4 r[4];
-                        if (K > 0) {
-                            uint4 d[SD];
-                            column_load<KD, true>(sbase + (size_t)col * 16, p.stride, ps.src_off, q, d);
-                            column_compute<KD>(d, tab_base, lane, p.row_bytes, tail, r);
-                        } else {
-                            column_rows_generic<true>(sbase + (size_t)col * 16, p.stride, k, ps.src_off, tab_base,
-                                                      p.row_bytes, tail, lane, r);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            if (i < rows) stg_stream(dbase + ps.dst_off[i] + (size_t)col * 16, r[i]);
-                    }
+                    for (int i = 0; i < 4; i++)
+                        if (i < cur.rows) stg_stream(dbase + ps.dst_off[i] + (size_t)col * 16, r[i]);
                 }
             }
-            __syncthreads();  // tables and slot `cs` are free again
+            if (pos != cur.seq) leave(cur.seq);  // the search moved on while these lookups were pending
+            pend = kNone;
+            if (!nx.valid && !ended) {  // the look-ahead was not allowed to go further: continue now
+                find(kNone, nx);
+                if (nx.valid) fetch(nx);
+            }
         }
     }
 }
