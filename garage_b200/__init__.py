@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "garage_ec_launch_count", "garage_ec_set_timing", "garage_ec_timing_read",
     "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
     "garage_ec_encode_blocks_with_sums", "garage_ec_scrub_repair",
+    "garage_ec_numa_info", "garage_ec_bind_thread", "garage_ec_debug_fail_after",
 ]
 
 
@@ -100,6 +101,9 @@ def load_library(build=True):
     L.garage_ec_launch_count.restype = u64
     L.garage_ec_set_timing.argtypes = [vp, i32]
     L.garage_ec_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.garage_ec_numa_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.garage_ec_bind_thread.argtypes = [vp]
+    L.garage_ec_debug_fail_after.argtypes = [vp, C.c_long]
     _lib = L
     return L
 
@@ -279,3 +283,16 @@ class GarageEc:
 
     def host_free(self, p):
         self._L.garage_ec_host_free(self._h, p)
+
+    def numa_info(self):
+        """(NUMA node of the GPU, node the last host_alloc landed on); -1 = unknown"""
+        a, b = C.c_int(-1), C.c_int(-1)
+        self._check(self._L.garage_ec_numa_info(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def bind_thread(self):
+        """pin the calling thread to the CPUs of the GPU's NUMA node; True if bound"""
+        return self._L.garage_ec_bind_thread(self._h) == 0
+
+    def debug_fail_after(self, n_calls):
+        self._check(self._L.garage_ec_debug_fail_after(self._h, n_calls))

@@ -7,8 +7,15 @@
 
 #include <cuda_runtime.h>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <atomic>
+#include <condition_variable>
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -35,6 +42,12 @@ struct HostLane {
     uint8_t *d_small = nullptr;  // shard_len / present / want / status / mismatch / plan
     size_t small_cap = 0;
 };
+// One HOST-mode call owns one set of lanes for its duration; concurrent callers (tokio
+// spawn_blocking threads, src/block/block.rs:86) get different sets, up to kMaxLaneSets.
+struct LaneSet {
+    HostLane lanes[kHostLanes];
+};
+constexpr int kMaxLaneSets = 4;
 
 }  // namespace
 
@@ -43,8 +56,16 @@ struct garage_ec_ctx {
     uint8_t P[kMaxM * kMaxK] = {0};
     int sm_count = 0;
     size_t smem_optin = 0;
-    std::mutex host_mu;  // serialises HOST-mode calls (they share the lanes)
-    HostLane lanes[kHostLanes];
+    std::mutex pool_mu;  // lane-set pool of the HOST-mode calls
+    std::condition_variable pool_cv;
+    std::vector<LaneSet *> free_sets;
+    int n_sets = 0;
+    // NUMA placement of the GPU (from sysfs): host memory for DMA should live on this node
+    int numa_node = -1;
+    bool have_node_cpus = false;
+    cpu_set_t node_cpus;
+    int last_alloc_node = -1;                 // node the last garage_ec_host_alloc landed on (-1 unknown)
+    std::atomic<long> fault_countdown{-1};    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
     std::mutex misc_mu;  // timing list, last_error
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -66,11 +87,118 @@ int set_cuda_error(garage_ec_ctx *ctx, cudaError_t e, const char *what)
     return e == cudaErrorMemoryAllocation ? GARAGE_EC_E_NOMEM : GARAGE_EC_E_CUDA;
 }
 
-#define CU_TRY(ctx, expr)                                          \
-    do {                                                           \
-        cudaError_t e__ = (expr);                                  \
-        if (e__ != cudaSuccess) return set_cuda_error(ctx, e__, #expr); \
+// test hook (garage_ec_debug_fail_after): the n-th checked runtime call from now fails
+inline bool fault_hit(garage_ec_ctx *ctx)
+{
+    if (!ctx || ctx->fault_countdown.load(std::memory_order_relaxed) < 0) return false;
+    return ctx->fault_countdown.fetch_sub(1, std::memory_order_relaxed) == 0;
+}
+
+#define CU_TRY(ctx, expr)                                                                          \
+    do {                                                                                           \
+        if (fault_hit(ctx)) return set_cuda_error(ctx, cudaErrorUnknown, "injected fault at " #expr); \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return set_cuda_error(ctx, e__, #expr);                            \
     } while (0)
+
+// Lease of one lane set for the duration of a HOST-mode call.  The destructor waits for every
+// lane stream BEFORE the set goes back to the pool -- and therefore before the entry point
+// returns, on every path including the early error returns: no DMA touches the caller's buffers
+// after a HOST call has returned ("the library keeps no pointer", include/garage_ec.h).
+struct LaneLease {
+    garage_ec_ctx *ctx;
+    LaneSet *set = nullptr;
+    explicit LaneLease(garage_ec_ctx *c) : ctx(c)
+    {
+        std::unique_lock<std::mutex> lk(ctx->pool_mu);
+        ctx->pool_cv.wait(lk, [&] { return !ctx->free_sets.empty() || ctx->n_sets < kMaxLaneSets; });
+        if (!ctx->free_sets.empty()) {
+            set = ctx->free_sets.back();
+            ctx->free_sets.pop_back();
+        } else {
+            set = new (std::nothrow) LaneSet();
+            if (set) ctx->n_sets++;
+        }
+    }
+    ~LaneLease()
+    {
+        if (!set) return;
+        for (HostLane &L : set->lanes)
+            if (L.stream) (void)cudaStreamSynchronize(L.stream);
+        (void)cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(ctx->pool_mu);
+            ctx->free_sets.push_back(set);
+        }
+        ctx->pool_cv.notify_one();
+    }
+    LaneLease(const LaneLease &) = delete;
+    LaneLease &operator=(const LaneLease &) = delete;
+    HostLane &operator[](size_t i) { return set->lanes[i]; }
+};
+#define LEASE_LANES(ctx, name)  \
+    LaneLease name(ctx);        \
+    if (!name.set) return GARAGE_EC_E_NOMEM
+
+// ---- NUMA placement of the GPU ------------------------------------------------------------
+// 8-GPU hosts hang 4 GPUs off each socket; pinned buffers that land on the other socket cross
+// the inter-socket link on every DMA (round 1: e2e weak scaling 0.65 at 8 GPUs with unplaced
+// buffers).  The node comes from sysfs, the CPU list of the node likewise; no libnuma.
+#ifndef MPOL_PREFERRED
+#define MPOL_DEFAULT 0
+#define MPOL_PREFERRED 1
+#endif
+bool read_small_file(const char *path, char *buf, size_t cap)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    const size_t n = fread(buf, 1, cap - 1, f);
+    fclose(f);
+    buf[n] = 0;
+    return n > 0;
+}
+bool parse_cpulist(const char *s, cpu_set_t *out)
+{
+    CPU_ZERO(out);
+    bool any = false;
+    while (*s) {
+        while (*s == ',' || isspace((unsigned char)*s)) s++;
+        if (!isdigit((unsigned char)*s)) break;
+        char *e;
+        long a = strtol(s, &e, 10), b = a;
+        if (*e == '-') b = strtol(e + 1, &e, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) {
+            CPU_SET((int)c, out);
+            any = true;
+        }
+        s = e;
+    }
+    return any;
+}
+void probe_numa(garage_ec_ctx *ctx)
+{
+    char busid[64] = {0}, path[160], buf[4096];
+    if (cudaDeviceGetPCIBusId(busid, sizeof(busid), ctx->device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    for (char *c = busid; *c; c++) *c = (char)tolower((unsigned char)*c);
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", busid);
+    if (!read_small_file(path, buf, sizeof(buf))) return;
+    const int node = atoi(buf);
+    if (node < 0) return;
+    ctx->numa_node = node;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    if (read_small_file(path, buf, sizeof(buf))) ctx->have_node_cpus = parse_cpulist(buf, &ctx->node_cpus);
+}
+// node a page lives on (move_pages with nodes == NULL only queries), -1 if unknown
+int node_of_page(void *p)
+{
+    int status = -1;
+    void *pages[1] = {p};
+    if (syscall(SYS_move_pages, 0, 1ul, pages, nullptr, &status, 0) != 0) return -1;
+    return status;
+}
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -267,6 +395,12 @@ struct CopyBatch {
     {
         const size_t cnt = dst.size();
         if (!cnt) return GARAGE_EC_OK;
+        if (fault_hit(ctx)) {
+            dst.clear();
+            src.clear();
+            sz.clear();
+            return set_cuda_error(ctx, cudaErrorUnknown, "injected fault at batched copy");
+        }
         bool done = false;
         if (cnt > 1 && ctx->batch_copy_ok.load(std::memory_order_relaxed)) {
             cudaMemcpyAttributes attr;
@@ -345,6 +479,7 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
         delete ctx;
         return GARAGE_EC_E_NODEVICE;
     }
+    probe_numa(ctx);
     *out = ctx;
     return GARAGE_EC_OK;
 }
@@ -394,13 +529,16 @@ void garage_ec_destroy(garage_ec_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (HostLane &L : ctx->lanes) {
-        if (L.stream) {
-            cudaStreamSynchronize(L.stream);
-            cudaStreamDestroy(L.stream);
+    for (LaneSet *set : ctx->free_sets) {
+        for (HostLane &L : set->lanes) {
+            if (L.stream) {
+                cudaStreamSynchronize(L.stream);
+                cudaStreamDestroy(L.stream);
+            }
+            if (L.d_buf) cudaFree(L.d_buf);
+            if (L.d_small) cudaFree(L.d_small);
         }
-        if (L.d_buf) cudaFree(L.d_buf);
-        if (L.d_small) cudaFree(L.d_small);
+        delete set;
     }
     for (auto &pr : ctx->pending) {
         cudaEventDestroy(pr.first);
@@ -485,8 +623,49 @@ int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes)
 {
     if (!ctx || !out || !bytes) return GARAGE_EC_E_INVALID;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    CU_TRY(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    // Place the pages on the GPU's NUMA node: the driver allocates and pins them inside this call,
+    // under the calling thread's memory policy and CPU.  Both are set for the duration of the call
+    // (preferred-node policy; where the sandbox forbids set_mempolicy, running on a CPU of the node
+    // gives the same result through the default local-allocation policy) and restored afterwards.
+    cpu_set_t saved_cpus;
+    bool moved = false, policy_set = false;
+    if (ctx->numa_node >= 0) {
+        unsigned long mask[16] = {0};
+        if (ctx->numa_node < (int)(sizeof(mask) * 8)) {
+            mask[ctx->numa_node / (8 * sizeof(unsigned long))] |= 1ul << (ctx->numa_node % (8 * sizeof(unsigned long)));
+            policy_set = syscall(SYS_set_mempolicy, MPOL_PREFERRED, mask, sizeof(mask) * 8) == 0;
+        }
+        if (ctx->have_node_cpus && sched_getaffinity(0, sizeof(saved_cpus), &saved_cpus) == 0) {
+            cpu_set_t want;
+            CPU_AND(&want, &saved_cpus, &ctx->node_cpus);
+            if (CPU_COUNT(&want) > 0 && sched_setaffinity(0, sizeof(want), &want) == 0) moved = true;
+        }
+    }
+    cudaError_t e = fault_hit(ctx) ? cudaErrorMemoryAllocation : cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (moved) sched_setaffinity(0, sizeof(saved_cpus), &saved_cpus);
+    if (policy_set) syscall(SYS_set_mempolicy, MPOL_DEFAULT, nullptr, 0ul);
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaHostAlloc");
+    ctx->last_alloc_node = node_of_page(*out);
     return GARAGE_EC_OK;
+}
+
+int garage_ec_numa_info(const garage_ec_ctx *ctx, int *gpu_node, int *last_alloc_node)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    if (gpu_node) *gpu_node = ctx->numa_node;
+    if (last_alloc_node) *last_alloc_node = ctx->last_alloc_node;
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_bind_thread(const garage_ec_ctx *ctx)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    if (ctx->numa_node < 0 || !ctx->have_node_cpus) return 1;  // nothing known: leave the thread alone
+    cpu_set_t cur, want;
+    if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return 1;
+    CPU_AND(&want, &cur, &ctx->node_cpus);
+    if (CPU_COUNT(&want) == 0) return 1;  // the cgroup does not allow any CPU of that node
+    return sched_setaffinity(0, sizeof(want), &want) == 0 ? GARAGE_EC_OK : 1;
 }
 
 void garage_ec_host_free(garage_ec_ctx *ctx, void *ptr)
@@ -515,19 +694,19 @@ int garage_ec_fill_random(garage_ec_ctx *ctx, uint8_t *dst_device, size_t len, u
 static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
                        const uint32_t *shard_len, size_t stride, size_t n)
 {
-    std::lock_guard<std::mutex> g(ctx->host_mu);
+    LEASE_LANES(ctx, lanes);
     const size_t k = ctx->k, m = ctx->m;
     size_t cs = kHostChunkBytes / (k * stride);
     if (cs < 1) cs = 1;
     if (cs > n) cs = n;
     const size_t in_b = cs * k * stride, out_b = cs * m * stride;
-    for (HostLane &L : ctx->lanes) {
+    for (HostLane &L : lanes.set->lanes) {
         int rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16));
         if (rc) return rc;
     }
     size_t c = 0;
     for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
-        HostLane &L = ctx->lanes[c % kHostLanes];
+        HostLane &L = lanes[c % kHostLanes];
         const size_t cnt = n - s0 < cs ? n - s0 : cs;
         CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, data + s0 * k * stride, cnt * k * stride,
                                     cudaMemcpyHostToDevice, L.stream));
@@ -543,7 +722,7 @@ static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
         CU_TRY(ctx, cudaMemcpyAsync(parity + s0 * m * stride, L.d_buf + in_b, cnt * m * stride,
                                     cudaMemcpyDeviceToHost, L.stream));
     }
-    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     return GARAGE_EC_OK;
 }
 
@@ -568,19 +747,19 @@ int garage_ec_encode(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
 static int verify_host(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismatch,
                        const uint32_t *shard_len, size_t stride, size_t n)
 {
-    std::lock_guard<std::mutex> g(ctx->host_mu);
+    LEASE_LANES(ctx, lanes);
     const size_t tot = ctx->k + ctx->m;
     size_t cs = kHostChunkBytes / (tot * stride);
     if (cs < 1) cs = 1;
     if (cs > n) cs = n;
     const size_t small = align_up(cs * 4, 16);
-    for (HostLane &L : ctx->lanes) {
+    for (HostLane &L : lanes.set->lanes) {
         int rc = lane_reserve(ctx, L, cs * tot * stride, 2 * small);
         if (rc) return rc;
     }
     size_t c = 0;
     for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
-        HostLane &L = ctx->lanes[c % kHostLanes];
+        HostLane &L = lanes[c % kHostLanes];
         const size_t cnt = n - s0 < cs ? n - s0 : cs;
         CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, shards + s0 * tot * stride, cnt * tot * stride,
                                     cudaMemcpyHostToDevice, L.stream));
@@ -597,7 +776,7 @@ static int verify_host(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mism
         if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(mismatch + s0, d_mm, cnt * 4, cudaMemcpyDeviceToHost, L.stream));
     }
-    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     return GARAGE_EC_OK;
 }
 
@@ -625,7 +804,10 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
                             const uint8_t *want, int32_t *status, const uint32_t *shard_len,
                             size_t stride, size_t n)
 {
-    std::lock_guard<std::mutex> g(ctx->host_mu);
+    // declared before the lane lease: they must outlive the stream work the lease waits for
+    std::vector<int32_t> st_host(status ? 0 : n);
+    CopyBatch up, down;
+    LEASE_LANES(ctx, lanes);
     const size_t k = ctx->k, tot = ctx->k + ctx->m;
     size_t cs = kHostChunkBytes / (tot * stride);
     if (cs < 1) cs = 1;
@@ -634,17 +816,15 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
     const size_t o_present = 0, o_want = align_up(cs * tot, 16), o_status = o_want + align_up(cs * tot, 16);
     const size_t o_len = o_status + align_up(cs * 4, 16), o_plan = o_len + align_up(cs * 4, 16);
     const size_t small = o_plan + plan_scratch_bytes(cs);
-    for (HostLane &L : ctx->lanes) {
+    for (HostLane &L : lanes.set->lanes) {
         int rc = lane_reserve(ctx, L, cs * tot * stride, small);
         if (rc) return rc;
     }
-    std::vector<int32_t> st_host(status ? 0 : n);
     int32_t *st_out = status ? status : st_host.data();
-    CopyBatch up, down;
     int rc = GARAGE_EC_OK;
     size_t c = 0;
     for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
-        HostLane &L = ctx->lanes[c % kHostLanes];
+        HostLane &L = lanes[c % kHostLanes];
         const size_t cnt = n - s0 < cs ? n - s0 : cs;
         uint8_t *d_sh = L.d_buf;
         // H2D: only the k survivors (first k present shards) of stripes that have work to do
@@ -704,7 +884,7 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
         rc = down.flush(ctx, cudaMemcpyDeviceToHost, L.stream);
         if (rc) return rc;
     }
-    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     for (size_t s = 0; s < n; s++)
         if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
     return GARAGE_EC_OK;
@@ -791,19 +971,19 @@ static int sums_common(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t 
         return run_sums(ctx, shards, expect, shard_len, stride, n * per, per, sums_out, bad_out,
                         (cudaStream_t)cuda_stream);
     // HOST: chunked through the lanes (H2D shards [+ expect], kernel, D2H sums / bad flags)
-    std::lock_guard<std::mutex> g(ctx->host_mu);
+    LEASE_LANES(ctx, lanes);
     size_t cs = kHostChunkBytes / ((size_t)per * stride);
     if (cs < 1) cs = 1;
     if (cs > n) cs = n;
     const size_t o_len = 0, o_exp = align_up(cs * 4, 16), o_sum = o_exp + cs * per * 32, o_bad = o_sum + cs * per * 32;
     const size_t small = o_bad + align_up(cs * per, 16);
-    for (HostLane &L : ctx->lanes) {
+    for (HostLane &L : lanes.set->lanes) {
         rc = lane_reserve(ctx, L, cs * per * stride, small);
         if (rc) return rc;
     }
     size_t c = 0;
     for (size_t s0 = 0; s0 < n; s0 += cs, c++) {
-        HostLane &L = ctx->lanes[c % kHostLanes];
+        HostLane &L = lanes[c % kHostLanes];
         const size_t cnt = n - s0 < cs ? n - s0 : cs;
         CU_TRY(ctx, cudaMemcpyAsync(L.d_buf, shards + s0 * per * stride, cnt * per * stride, cudaMemcpyHostToDevice,
                                     L.stream));
@@ -828,7 +1008,7 @@ static int sums_common(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t 
             CU_TRY(ctx, cudaMemcpyAsync(bad_out + s0 * per, L.d_small + o_bad, cnt * per, cudaMemcpyDeviceToHost,
                                         L.stream));
     }
-    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     return GARAGE_EC_OK;
 }
 
@@ -884,28 +1064,28 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
     // HOST: every shard goes up (it has to be hashed); only the rebuilt shards come back.  The
     // rebuilt set is known once the bad flags are on the host, so each lane's chunk is finished
     // (flags read, copies issued) when the lane comes round again.
-    std::lock_guard<std::mutex> g(ctx->host_mu);
+    std::vector<int32_t> st_host(status ? 0 : n_stripes);  // outlives the lane lease below
+    CopyBatch down;
+    LEASE_LANES(ctx, lanes);
     size_t cs = kHostChunkBytes / (tot * stride);
     if (cs < 1) cs = 1;
     if (cs > n_stripes) cs = n_stripes;
     const size_t o_exp = 0, o_bad = o_exp + cs * tot * 32, o_status = o_bad + align_up(cs * tot, 16);
     const size_t o_len = o_status + align_up(cs * 4, 16), o_plan = o_len + align_up(cs * 4, 16);
     const size_t small = o_plan + plan_scratch_bytes(cs);
-    for (HostLane &L : ctx->lanes) {
+    for (HostLane &L : lanes.set->lanes) {
         rc = lane_reserve(ctx, L, cs * tot * stride, small);
         if (rc) return rc;
     }
-    std::vector<int32_t> st_host(status ? 0 : n_stripes);
     int32_t *st_out = status ? status : st_host.data();
     struct Pending {
         bool active = false;
         size_t s0 = 0, cnt = 0;
     } pend[kHostLanes];
-    CopyBatch down;
     auto finish = [&](size_t lane_i) -> int {
         Pending &P = pend[lane_i];
         if (!P.active) return GARAGE_EC_OK;
-        HostLane &L = ctx->lanes[lane_i];
+        HostLane &L = lanes[lane_i];
         CU_TRY(ctx, cudaStreamSynchronize(L.stream));  // bad flags + status of this chunk are on the host
         for (size_t s = P.s0; s < P.s0 + P.cnt; s++) {
             if (st_out[s] != 0) continue;
@@ -922,7 +1102,7 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
     size_t c = 0;
     for (size_t s0 = 0; s0 < n_stripes; s0 += cs, c++) {
         const size_t lane_i = c % kHostLanes;
-        HostLane &L = ctx->lanes[lane_i];
+        HostLane &L = lanes[lane_i];
         rc = finish(lane_i);
         if (rc) return rc;
         const size_t cnt = n_stripes - s0 < cs ? n_stripes - s0 : cs;
@@ -953,7 +1133,7 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
         rc = finish(l);
         if (rc) return rc;
     }
-    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     for (size_t s = 0; s < n_stripes; s++)
         if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
     return GARAGE_EC_OK;
@@ -999,21 +1179,21 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         if (garage_ec_shard_len(block_len[s], (int)k) > stride) return GARAGE_EC_E_INVALID;
     }
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->host_mu);
     size_t cs = kHostChunkBytes / (k * stride);
     if (cs < 1) cs = 1;
     if (cs > n_blocks) cs = n_blocks;
+    std::vector<uint32_t> lens(cs * kHostLanes);  // outlives the lane lease below
+    LEASE_LANES(ctx, lanes);
     const size_t in_b = cs * k * stride, out_b = cs * m * stride;
-    for (HostLane &L : ctx->lanes) {
+    for (HostLane &L : lanes.set->lanes) {
         rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16) + cs * (k + m) * 32);
         if (rc) return rc;
     }
     const size_t o_sums = align_up(cs * 4, 16);
-    std::vector<uint32_t> lens(cs * kHostLanes);
     size_t c = 0;
     for (size_t s0 = 0; s0 < n_blocks; s0 += cs, c++) {
         const size_t lane_i = c % kHostLanes;
-        HostLane &L = ctx->lanes[lane_i];
+        HostLane &L = lanes[lane_i];
         const size_t cnt = n_blocks - s0 < cs ? n_blocks - s0 : cs;
         // the pageable `lens` slot of this lane is reused: wait for the lane's previous chunk
         if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
@@ -1040,7 +1220,7 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
                                         cudaMemcpyDeviceToHost, L.stream));
         }
     }
-    for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     return GARAGE_EC_OK;
 }
 
@@ -1056,7 +1236,6 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
     if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
     const size_t k = ctx->k, tot = ctx->k + ctx->m;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> g(ctx->host_mu);
 
     // stripes with an absent data shard go to the GPU; the rest is a host-side join
     std::vector<size_t> need;
@@ -1083,15 +1262,18 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
         const size_t o_present = 0, o_want = align_up(cs * tot, 16), o_status = o_want + align_up(cs * tot, 16);
         const size_t o_len = o_status + align_up(cs * 4, 16), o_plan = o_len + align_up(cs * 4, 16);
         const size_t small = o_plan + plan_scratch_bytes(cs);
-        for (HostLane &L : ctx->lanes) {
+        // host staging and copy lists are declared before the lane lease: they outlive its stream work
+        std::vector<uint8_t> h_small((2 * cs * tot + cs * 4) * kHostLanes);
+        CopyBatch up, down;
+        LEASE_LANES(ctx, lanes);
+        for (HostLane &L : lanes.set->lanes) {
             rc = lane_reserve(ctx, L, cs * tot * stride, small);
             if (rc) return rc;
         }
-        std::vector<uint8_t> h_small((2 * cs * tot + cs * 4) * kHostLanes);
         size_t c = 0;
         for (size_t q0 = 0; q0 < need.size(); q0 += cs, c++) {
             const size_t lane_i = c % kHostLanes;
-            HostLane &L = ctx->lanes[lane_i];
+            HostLane &L = lanes[lane_i];
             const size_t cnt = need.size() - q0 < cs ? need.size() - q0 : cs;
             if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
             uint8_t *hp = h_small.data() + lane_i * (2 * cs * tot + cs * 4);
@@ -1102,9 +1284,17 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
                 memcpy(hp + q * tot, present + s * tot, tot);
                 for (size_t i = 0; i < tot; i++) hw[q * tot + i] = i < k ? 1 : 0;  // data shards only
                 hl[q] = garage_ec_shard_len(block_len[s], (int)k);
-                CU_TRY(ctx, cudaMemcpyAsync(L.d_buf + q * tot * stride, shards + s * tot * stride,
-                                            tot * stride, cudaMemcpyHostToDevice, L.stream));
+                // H2D: only the k survivors the kernel reads (the first k present shards) -- the
+                // GET path is PCIe-bound, absent and surplus shards stay on the host
+                size_t used = 0;
+                for (size_t i = 0; i < tot && used < k; i++) {
+                    if (!present[s * tot + i]) continue;
+                    up.add(L.d_buf + (q * tot + i) * stride, shards + (s * tot + i) * stride, align_up(hl[q], 16));
+                    used++;
+                }
             }
+            rc = up.flush(ctx, cudaMemcpyHostToDevice, L.stream);
+            if (rc) return rc;
             CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_present, hp, cnt * tot, cudaMemcpyHostToDevice, L.stream));
             CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_want, hw, cnt * tot, cudaMemcpyHostToDevice, L.stream));
             CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_len, hl, cnt * 4, cudaMemcpyHostToDevice, L.stream));
@@ -1124,13 +1314,31 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
                     const size_t off = j * Ls;
                     if (off >= block_len[s]) continue;
                     const size_t have = block_len[s] - off < Ls ? block_len[s] - off : Ls;
-                    CU_TRY(ctx, cudaMemcpyAsync(blocks_out[s] + off, L.d_buf + (q * tot + j) * stride, have,
-                                                cudaMemcpyDeviceToHost, L.stream));
+                    down.add(blocks_out[s] + off, L.d_buf + (q * tot + j) * stride, have);
                 }
             }
+            rc = down.flush(ctx, cudaMemcpyDeviceToHost, L.stream);
+            if (rc) return rc;
         }
+        // host-side join of the data shards that did arrive, while the GPU works
+        // (framing: block = shard0|shard1|...)
+        for (size_t s = 0; s < n_blocks; s++) {
+            const uint8_t *pr = present + s * tot;
+            size_t np = 0;
+            for (size_t i = 0; i < tot; i++) np += pr[i] ? 1 : 0;
+            if (np < k) continue;
+            const size_t Ls = garage_ec_shard_len(block_len[s], (int)k);
+            for (size_t j = 0; j < k; j++) {
+                if (!pr[j]) continue;
+                const size_t off = j * Ls;
+                if (off >= block_len[s]) continue;
+                const size_t have = block_len[s] - off < Ls ? block_len[s] - off : Ls;
+                memcpy(blocks_out[s] + off, shards + (s * tot + j) * stride, have);
+            }
+        }
+        for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        return any_bad ? GARAGE_EC_E_UNRECOVERABLE : GARAGE_EC_OK;
     }
-    // host-side join of the data shards that did arrive (framing: block = shard0|shard1|...)
     for (size_t s = 0; s < n_blocks; s++) {
         const uint8_t *pr = present + s * tot;
         size_t np = 0;
@@ -1138,16 +1346,21 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
         if (np < k) continue;
         const size_t Ls = garage_ec_shard_len(block_len[s], (int)k);
         for (size_t j = 0; j < k; j++) {
-            if (!pr[j]) continue;
             const size_t off = j * Ls;
             if (off >= block_len[s]) continue;
             const size_t have = block_len[s] - off < Ls ? block_len[s] - off : Ls;
             memcpy(blocks_out[s] + off, shards + (s * tot + j) * stride, have);
         }
     }
-    if (!need.empty())
-        for (HostLane &L : ctx->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
     return any_bad ? GARAGE_EC_E_UNRECOVERABLE : GARAGE_EC_OK;
+}
+
+// ---- test hook -------------------------------------------------------------------------------
+int garage_ec_debug_fail_after(garage_ec_ctx *ctx, long n_calls)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    ctx->fault_countdown.store(n_calls, std::memory_order_relaxed);
+    return GARAGE_EC_OK;
 }
 
 }  // extern "C"

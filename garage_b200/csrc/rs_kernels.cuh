@@ -72,6 +72,9 @@ namespace garage_ec {
 #ifndef GEC_NW_VER
 #define GEC_NW_VER 0
 #endif
+#ifndef GEC_LDG_MAXLG
+#define GEC_LDG_MAXLG 3  // LDG path: largest table group = 2^3 tables (64 contiguous bytes per shard and instruction)
+#endif
 #ifndef GEC_TMA_FROM_K
 #define GEC_TMA_FROM_K 13  // encode / reconstruct use the TMA staging from this k on
 #endif
@@ -176,6 +179,12 @@ __host__ __device__ constexpr int cfg_nw_tma(int regs_est, uint32_t tab_bytes, i
     return nw;
 }
 
+__host__ __device__ constexpr int cfg_fit_nw(int nw, uint32_t tab_bytes, int stage_rows, bool builder)
+{
+    while (nw > 4 && tab_bytes + kAuxBytes + (uint32_t)(nw - (builder ? 1 : 0)) * stage_rows * kStageRowBytes > kSmemLimit) nw -= 4;
+    return nw;
+}
+
 // ---- launch shape / shared-memory carve-up per (K, MODE), all compile time ------------------
 template <int K, int MODE> struct StreamCfg {
     static constexpr int kTmaOverride = MODE == kModeEncode ? GEC_TMA_ENC : (MODE == kModePlan ? GEC_TMA_PLAN : GEC_TMA_VER);
@@ -187,7 +196,7 @@ template <int K, int MODE> struct StreamCfg {
     // LDG: groups of <= 8 tables (>= 64 contiguous bytes per shard and warp instruction), tables
     // <= 192 KB so that >= 32 KB stay L1 (round 1: 224 KB of tables starved the global loads).
     // TMA: groups of <= 32 tables, <= 3 groups per buffer; the loads bypass L1.
-    static constexpr int kMaxLg = kTma ? 5 : 3;
+    static constexpr int kMaxLg = kTma ? 5 : GEC_LDG_MAXLG;
     static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows) : 6 / kBufs;
     static constexpr TabLayout kLay = make_layout(K, kMaxLg, kMaxGrp);
     static constexpr int S = kLay.nslots;
@@ -196,7 +205,9 @@ template <int K, int MODE> struct StreamCfg {
     // consumer warps: LDG shapes from the round-1 sweeps (2 x S x 4 registers of column data);
     // TMA: S x 4 registers of column data, capped by the stage memory
     static constexpr int kWarpsDefault = kTma ? cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows) : cfg_nw_ldg(K, MODE);
-    static constexpr int kWarpsAll = kNwOverride > 0 ? kNwOverride : kWarpsDefault;
+    // an override (tuning builds) is clamped to what the stage memory allows
+    static constexpr int kWarpsAll =
+        kNwOverride > 0 ? (kTma ? cfg_fit_nw(kNwOverride, kTabBytes, kStageRows, MODE == kModePlan) : kNwOverride) : kWarpsDefault;
     // reconstruct: the last warp is the table builder
     static constexpr int kWarps = MODE == kModePlan ? kWarpsAll - 1 : kWarpsAll;  // consumer warps
     static constexpr int kThreads = 32 * kWarpsAll;
@@ -572,8 +583,8 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
     if (tid == 0) {
         mbar_init(bar_full, 32);
         mbar_init(bar_full + 8, 32);
-        mbar_init(bar_empty, NW);
-        mbar_init(bar_empty + 8, NW);
+        mbar_init(bar_empty, NW * 32);
+        mbar_init(bar_empty + 8, NW * 32);
     }
     if (TMA && lane == 0 && warp < (uint32_t)NW) mbar_init(bar_stage, 1);
     mbar_fence_init();
@@ -787,10 +798,9 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
             int rows;
             bool valid;
         };
-        auto leave = [&](uint32_t i) {  // this warp will not touch tables / slot of sequence i again
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * (i & 1));
-        };
+        // this warp will not touch tables / slot of sequence i again (every lane arrives: each
+        // lane's own reads are ordered before its own release)
+        auto leave = [&](uint32_t i) { mbar_arrive(bar_empty + 8 * (i & 1)); };
         // next work item of this warp; never waits for full[j] with j > lim (the builder may need
         // this warp's `leave` of an older stripe first)
         auto find = [&](uint32_t lim, It &it) {

@@ -186,6 +186,17 @@ int garage_ec_fill_random(garage_ec_ctx *ctx, uint8_t *dst_device, size_t len, u
  * engines can read it.  Pageable memory is accepted everywhere, only slower.               */
 int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes);
 void garage_ec_host_free(garage_ec_ctx *ctx, void *ptr);
+/* NUMA placement.  On a multi-socket host each GPU hangs off one socket; garage_ec_host_alloc
+ * places its pages on that socket's memory node (preferred-node policy + first touch from a CPU
+ * of the node, both restored before returning), so DMA never crosses the inter-socket link.
+ * garage_ec_numa_info reports the GPU's node and the node the last garage_ec_host_alloc of this
+ * context landed on (-1 = unknown).  garage_ec_bind_thread pins the CALLING thread to the CPUs
+ * of the GPU's node -- for the threads that fill those buffers (the batching workers in front of
+ * rpc_put_block / the 8 resync workers, src/block/resync.rs:43; spawn_blocking threads,
+ * src/block/block.rs:86): returns 0 if bound, 1 if nothing was changed (topology unknown or not
+ * permitted).                                                                               */
+int garage_ec_numa_info(const garage_ec_ctx *ctx, int *gpu_node, int *last_alloc_node);
+int garage_ec_bind_thread(const garage_ec_ctx *ctx);
 
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches)        */
 uint64_t garage_ec_launch_count(const garage_ec_ctx *ctx);
@@ -194,6 +205,11 @@ uint64_t garage_ec_launch_count(const garage_ec_ctx *ctx);
  * the recorded kernels, adds their durations to *total_ms / *launches and resets.          */
 int garage_ec_set_timing(garage_ec_ctx *ctx, int enabled);
 int garage_ec_timing_read(garage_ec_ctx *ctx, double *total_ms, uint64_t *launches);
+
+/* test hook: the n_calls-th checked CUDA runtime call issued by this context from now on fails
+ * (n_calls = 0: the next one; < 0: off).  Used by the fault-injection tests of the HOST-mode
+ * ownership contract: after a failed call returns, nothing may still write the caller's buffers. */
+int garage_ec_debug_fail_after(garage_ec_ctx *ctx, long n_calls);
 
 #ifdef __cplusplus
 }

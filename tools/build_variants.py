@@ -13,14 +13,21 @@ from garage_b200 import _build  # noqa: E402
 
 out_dir = os.path.join(ROOT, "build", "variants")
 os.makedirs(out_dir, exist_ok=True)
-procs = []
-for spec in sys.argv[1:]:
+from concurrent.futures import ThreadPoolExecutor  # noqa: E402
+
+
+def run(spec):
     name, flags = spec.split("=", 1)
     out = os.path.join(out_dir, "libgarage_ec_%s.so" % name)
     cmd = _build.nvcc_cmd(out=out, extra=tuple(f for f in flags.split(",") if f) + ("-Xptxas", "-v"))
-    procs.append((name, out, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-for name, out, p in procs:
-    txt = p.communicate()[0]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return name, out, p
+
+
+with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:
+    results = list(ex.map(run, sys.argv[1:]))
+for name, out, p in results:
+    txt = p.stdout
     if p.returncode:
         print(name, "FAILED\n", txt)
         continue
