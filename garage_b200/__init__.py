@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
     "garage_ec_encode_blocks_with_sums", "garage_ec_scrub_repair",
     "garage_ec_numa_info", "garage_ec_bind_thread", "garage_ec_debug_fail_after",
+    "garage_ec_set_sum_kind", "garage_ec_shard_sum_host",
 ]
 
 
@@ -104,6 +105,8 @@ def load_library(build=True):
     L.garage_ec_numa_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.garage_ec_bind_thread.argtypes = [vp]
     L.garage_ec_debug_fail_after.argtypes = [vp, C.c_long]
+    L.garage_ec_set_sum_kind.argtypes = [vp, i32]
+    L.garage_ec_shard_sum_host.argtypes = [i32, vp, sz, vp]
     _lib = L
     return L
 
@@ -114,6 +117,20 @@ def blake2sum(data) -> bytes:
     a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
     out = np.zeros(32, dtype=np.uint8)
     L.garage_ec_blake2sum(C.c_void_p(a.ctypes.data) if a.size else None, a.size, C.c_void_p(out.ctypes.data))
+    return out.tobytes()
+
+
+SUM_BLAKE2, SUM_ADLER8 = 0, 1
+
+
+def shard_sum_host(kind, data) -> bytes:
+    """the 32-byte per-shard tag of `kind` computed by the library's host code"""
+    L = load_library()
+    a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    out = np.zeros(32, dtype=np.uint8)
+    rc = L.garage_ec_shard_sum_host(kind, C.c_void_p(a.ctypes.data) if a.size else None, a.size, C.c_void_p(out.ctypes.data))
+    if rc:
+        raise EcError(rc, "shard_sum_host")
     return out.tobytes()
 
 
@@ -293,6 +310,9 @@ class GarageEc:
     def bind_thread(self):
         """pin the calling thread to the CPUs of the GPU's NUMA node; True if bound"""
         return self._L.garage_ec_bind_thread(self._h) == 0
+
+    def set_sum_kind(self, kind):
+        self._check(self._L.garage_ec_set_sum_kind(self._h, kind))
 
     def debug_fail_after(self, n_calls):
         self._check(self._L.garage_ec_debug_fail_after(self._h, n_calls))

@@ -123,4 +123,32 @@ inline void blake2sum_host(const uint8_t *data, size_t len, uint8_t out[32])
     memcpy(out, S.h, 32);
 }
 
+// adler8 shard tag, host side (same definition as adler8_shards_kernel in rs_kernels.cuh)
+inline void adler8_host(const uint8_t *data, size_t len, uint8_t out[32])
+{
+    const size_t seg = (((len + 7) / 8) + 15) / 16 * 16;
+    for (int s = 0; s < 8; s++) {
+        const size_t start = (size_t)s * seg;
+        uint32_t a = 1, b = 0;
+        if (start < len) {
+            const size_t end = len < start + seg ? len : start + seg;
+            size_t i = start;
+            while (i < end) {  // 5552: largest run whose sums cannot overflow 32 bits (zlib's NMAX)
+                const size_t stop = end - i > 5552 ? i + 5552 : end;
+                for (; i < stop; i++) {
+                    a += data[i];
+                    b += a;
+                }
+                a %= 65521;
+                b %= 65521;
+            }
+        }
+        const uint32_t v = (b << 16) | a;
+        out[4 * s + 0] = (uint8_t)v;
+        out[4 * s + 1] = (uint8_t)(v >> 8);
+        out[4 * s + 2] = (uint8_t)(v >> 16);
+        out[4 * s + 3] = (uint8_t)(v >> 24);
+    }
+}
+
 }  // namespace garage_ec

@@ -11,6 +11,7 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cctype>
@@ -61,6 +62,7 @@ struct garage_ec_ctx {
     std::vector<LaneSet *> free_sets;
     int n_sets = 0;
     // NUMA placement of the GPU (from sysfs): host memory for DMA should live on this node
+    std::atomic<int> sum_kind{GARAGE_EC_SUM_BLAKE2};  // per-shard integrity tag (garage_ec_set_sum_kind)
     int numa_node = -1;
     bool have_node_cpus = false;
     cpu_set_t node_cpus;
@@ -943,7 +945,11 @@ static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *ex
     // few shards: four lanes per shard (4x the parallelism, but the quad shuffles make it
     // LSU-bound: measured 5.4 ms vs 7.6 ms at 18 432 shards and 6.0 vs 5.7 ms at 28 672);
     // from ~24 000 shards on one thread per shard keeps the schedulers busy enough
-    if (n_shards < 24000)
+    if (ctx->sum_kind.load(std::memory_order_relaxed) == GARAGE_EC_SUM_ADLER8) {
+        // one warp per shard, 8 warps per block; a few blocks per SM keep enough loads in flight
+        const unsigned blocks = (unsigned)std::min<size_t>((n_shards + 7) / 8, (size_t)ctx->sm_count * 8);
+        adler8_shards_kernel<<<blocks, 256, 0, st>>>(q);
+    } else if (n_shards < 24000)
         blake2sum_shards_quad_kernel<<<(unsigned)((n_shards + kQuadThreads / 4 - 1) / (kQuadThreads / 4)), kQuadThreads, 0,
                                        st>>>(q);
     else
@@ -1030,6 +1036,22 @@ int garage_ec_check_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_
 }
 
 void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]) { blake2sum_host(data, len, out32); }
+
+int garage_ec_set_sum_kind(garage_ec_ctx *ctx, int kind)
+{
+    if (!ctx || (kind != GARAGE_EC_SUM_BLAKE2 && kind != GARAGE_EC_SUM_ADLER8)) return GARAGE_EC_E_INVALID;
+    ctx->sum_kind.store(kind, std::memory_order_relaxed);
+    return GARAGE_EC_OK;
+}
+
+int garage_ec_shard_sum_host(int kind, const uint8_t *data, size_t len, uint8_t out32[32])
+{
+    if (!out32 || (!data && len)) return GARAGE_EC_E_INVALID;
+    if (kind == GARAGE_EC_SUM_BLAKE2) blake2sum_host(data, len, out32);
+    else if (kind == GARAGE_EC_SUM_ADLER8) adler8_host(data, len, out32);
+    else return GARAGE_EC_E_INVALID;
+    return GARAGE_EC_OK;
+}
 
 // --------------------------------------------------------------------------- SCRUB + REPAIR
 int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *expect_sums, uint8_t *bad_out,

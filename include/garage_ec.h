@@ -150,6 +150,20 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
                            size_t stride, size_t n_stripes, int mem_kind, void *cuda_stream);
 /* host-side blake2sum of one buffer (the same function, for block hashes / small inputs)       */
 void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]);
+/* Which 32-byte tag the per-shard integrity calls of a context compute and compare
+ * (garage_ec_shard_sums / _check_sums / _scrub_repair / _encode_blocks_with_sums):
+ *   GARAGE_EC_SUM_BLAKE2 (default)  Garage's blake2sum of the shard (src/util/data.rs:130-138):
+ *                     cryptographic, compute-bound on the GPU (~0.5 TB/s).
+ *   GARAGE_EC_SUM_ADLER8  the shard cut in 8 segments of roundup16(ceil(len/8)) bytes, tag = the 8
+ *                     little-endian zlib Adler-32 values of the segments (empty segment: 1).  Catches
+ *                     bit rot, which is all scrub needs -- the block's content address stays its
+ *                     blake2sum -- and streams at HBM speed (SURVEY.md section 8 row f2 allows a cheap
+ *                     per-shard checksum).  The shard file header records which kind it carries.
+ * garage_ec_shard_sum_host computes either tag on the CPU (nodes without a GPU, single shards).   */
+#define GARAGE_EC_SUM_BLAKE2 0
+#define GARAGE_EC_SUM_ADLER8 1
+int garage_ec_set_sum_kind(garage_ec_ctx *ctx, int kind);
+int garage_ec_shard_sum_host(int kind, const uint8_t *data, size_t len, uint8_t out32[32]);
 
 /* ---- BLOCK-LEVEL convenience (host memory only) -----------------------------------------
  * What rpc_put_block hands over is a contiguous block (bytes::Bytes), not shards.  These do

@@ -330,7 +330,8 @@ def test_encode_decode_blocks_host(torch, k, m):
 @pytest.mark.parametrize("k,m,n", [(10, 4, 4096), (6, 3, 1024), (4, 2, 1024)])
 def test_full_size_roundtrip(torch, k, m, n):
     """BASELINE configs 2+3: encode n x 1 MiB blocks, erase m random shards per stripe,
-    reconstruct, compare with the originals; scrub says clean; sampled stripes == oracle."""
+    reconstruct, compare with the originals (every byte); scrub says clean; every parity byte of
+    every stripe == CPU oracle."""
     B = 1 << 20
     tot = k + m
     with G.GarageEc(0, k, m) as ec:
@@ -351,12 +352,22 @@ def test_full_size_roundtrip(torch, k, m, n):
         ec.encode(tmp, par, stride, n, shard_len=lens)
         sh3[:, k:] = par.view(n, m, stride)
         torch.cuda.synchronize()
-        # sampled stripes against the oracle
+        # EVERY parity byte of EVERY stripe against the CPU oracle: the multi-threaded
+        # SIMD arm computes all n stripes, and is itself held to the normative scalar oracle on a sample
         P = O.build_matrix(k, m, 0)
-        for s in list(range(0, n, max(1, n // 7))) + [n - 1]:
-            d = host(t3[s]).reshape(-1)
-            want = O.encode(k, m, P, d, stride, 1, np.array([L], dtype=np.uint32), simd=True)
-            assert np.array_equal(host(par.view(n, m, stride)[s]).reshape(-1), want), s
+        h_data = host(tmp)
+        h_lens = np.full(n, L, dtype=np.uint32)
+        want_all = O.encode(k, m, P, h_data, stride, n, h_lens, simd=True)
+        got_all = host(par)
+        assert got_all.shape == want_all.shape
+        if not np.array_equal(got_all, want_all):
+            badrow = np.flatnonzero((got_all.reshape(n, -1) != want_all.reshape(n, -1)).any(axis=1))
+            raise AssertionError("parity differs from the oracle in %d stripes, first %s" % (badrow.size, badrow[:8]))
+        for s in list(range(0, n, max(1, n // 13))) + [n - 1]:
+            d = h_data.reshape(n, k * stride)[s]
+            scalar = O.encode(k, m, P, d, stride, 1, np.array([L], dtype=np.uint32))
+            assert np.array_equal(want_all.reshape(n, m * stride)[s], scalar), ("simd arm vs scalar oracle", s)
+        del want_all, got_all, h_data
         # the device data is the documented stream (spot check one stripe against the CPU generator)
         assert np.array_equal(host(t3[3, 0, :L]), O.fill_random(L, SEED, (3 * k) * stride)[:L])
         # scrub: clean
