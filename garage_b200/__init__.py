@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
     "garage_ec_encode_blocks_with_sums", "garage_ec_scrub_repair",
     "garage_ec_numa_info", "garage_ec_bind_thread", "garage_ec_debug_fail_after",
-    "garage_ec_set_sum_kind", "garage_ec_shard_sum_host",
+    "garage_ec_set_sum_kind", "garage_ec_shard_sum_host", "garage_ec_reconstruct_stripes",
 ]
 
 
@@ -105,6 +105,7 @@ def load_library(build=True):
     L.garage_ec_numa_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.garage_ec_bind_thread.argtypes = [vp]
     L.garage_ec_debug_fail_after.argtypes = [vp, C.c_long]
+    L.garage_ec_reconstruct_stripes.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz]
     L.garage_ec_set_sum_kind.argtypes = [vp, i32]
     L.garage_ec_shard_sum_host.argtypes = [i32, vp, sz, vp]
     _lib = L
@@ -242,6 +243,14 @@ class GarageEc:
         return self._check(self._L.garage_ec_reconstruct(self._h, _ptr(shards), _ptr(present), _ptr(want),
                                                          _ptr(status), _ptr(shard_len), stride, n, kind, st),
                            allow)
+
+    def reconstruct_stripes(self, stripes, present, stride, want=None, status=None, shard_len=None):
+        """gather form: `stripes` is a list of numpy arrays, one (k+m)*stride buffer per stripe"""
+        n = len(stripes)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in stripes])
+        return self._check(self._L.garage_ec_reconstruct_stripes(self._h, C.cast(ptrs, C.c_void_p), _ptr(present),
+                                                                 _ptr(want), _ptr(status), _ptr(shard_len), stride, n),
+                           (E_UNRECOVERABLE,))
 
     def verify(self, shards, mismatch, stride, n, shard_len=None):
         kind, st = self._stream(shards)

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libgarage_ec.so")
 SOURCES = ["garage_ec.cu"]
-DEPS = ["garage_ec.cu", "rs_kernels.cuh", "gf256.h", "gf256_tables.inc"]
+DEPS = ["garage_ec.cu", "rs_kernels.cuh", "gf256.h", "gf256_tables.inc", "blake2b.h"]
 
 
 def nvcc_path():
@@ -76,8 +76,9 @@ def build(force=False, verbose=False):
 
 
 BM_SO = os.path.join(PKG, "libgarage_block.so")
-BM_DEPS = [os.path.join(CSRC, "block_manager.cpp"), os.path.join(ROOT, "include", "garage_block_manager.h"),
-           os.path.join(ROOT, "include", "garage_ec.h")]
+BM_SOURCES = [os.path.join(CSRC, "block_manager.cpp"), os.path.join(CSRC, "shard_wire.cpp")]
+BM_DEPS = BM_SOURCES + [os.path.join(ROOT, "include", "garage_block_manager.h"), os.path.join(ROOT, "include", "garage_ec.h"),
+                        os.path.join(ROOT, "include", "garage_shard_wire.h"), os.path.join(CSRC, "blake2b.h")]
 
 
 def build_block_manager(force=False):
@@ -92,7 +93,7 @@ def build_block_manager(force=False):
         return _wait_for(BM_SO)
     cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-Wall", "-Wextra",
-           "-I", os.path.join(ROOT, "include"), BM_DEPS[0], "-L", PKG, "-lgarage_ec",
+           "-I", os.path.join(ROOT, "include"), *BM_SOURCES, "-L", PKG, "-lgarage_ec",
            "-Wl,-rpath,$ORIGIN", "-o", BM_SO + ".tmp%d" % os.getpid()]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -6,7 +6,12 @@
 // Row f1 (batching front-end): rpc_put_block / reconstructing GETs / resync workers are called
 // from many threads (reference: <= 3 blocks in flight per PUT, src/api/s3/put.rs:42; 8 resync
 // workers, src/block/resync.rs:43).  One block per GPU call cannot amortise launch + PCIe
-// latency, so calls are queued and a dispatcher thread hands the GPU whole batches.
+// latency, so calls are queued and dispatcher threads hand the GPU whole batches.  Data movement
+// on the host is done by the CALLING threads, in parallel: a PUT lands its block in a pinned slot
+// and later stores its shards straight out of the dispatcher's pinned parity buffer; a degraded
+// GET / a resync worker reads the surviving shards from the node stores straight into its own
+// pinned stripe slot, and the batch handed to the GPU is a list of slot pointers
+// (garage_ec_reconstruct_stripes).  The dispatchers only issue the batch call.
 #include "../../include/garage_block_manager.h"
 #include "../../include/garage_ec.h"
 
@@ -15,25 +20,30 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstddef>
+#include <cstdio>
 #include <cstring>
 #include <deque>
-#include <cstdio>
 #include <filesystem>
 #include <functional>
 #include <future>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace {
 
 using Hash = std::array<uint8_t, 32>;
+using Clock = std::chrono::steady_clock;
 struct HashHasher {
     size_t operator()(const Hash &h) const
     {
@@ -50,27 +60,44 @@ Hash to_hash(const uint8_t *p)
     return h;
 }
 
+uint32_t adler32_small(const uint8_t *p, size_t n)
+{
+    uint32_t a = 1, b = 0;
+    for (size_t i = 0; i < n; i++) {
+        a = (a + p[i]) % 65521;
+        b = (b + a) % 65521;
+    }
+    return (b << 16) | a;
+}
+
 // ---------------------------------------------------------------- one node's local store
 // mirrors BlockManagerLocked::write_block_inner / find_block / read_block_from /
 // move_block_to_corrupted (src/block/manager.rs:720-819) with a map instead of a directory tree
-struct StoredShard {
-    int index = -1;          // which of the k+m shards (would be part of the file name / header, row f3)
+struct ShardMeta {
+    int index = -1;          // which of the k+m shards
     uint32_t block_len = 0;  // unpadded length of the whole block
+    uint32_t shard_len = 0;
+    uint8_t sum_kind = 0;    // GARAGE_EC_SUM_* of `sum`
+    Hash sum{};              // integrity tag of the shard bytes (row f2)
+};
+struct StoredShard : ShardMeta {
     std::vector<uint8_t> bytes;
-    Hash sum{};  // blake2sum of `bytes` (row f2)
 };
 
 // On-disk shard file (row f3; mirrors the tmp-file -> rename -> .corrupted life cycle of
 // BlockManagerLocked::write_block_inner / move_block_to_corrupted, src/block/manager.rs:720-819,
 // and the directory scheme data_dir/<h[0]>/<h[1]>/<hex(h)> of src/block/layout.rs:286-291):
 //   <data_dir>/node<N>/<hh>/<hh>/<64 hex>.shard        64-byte header + shard bytes
+// hdr_check covers the first 48 bytes (every field a reader acts on), so a flipped index /
+// block_len / sum kind is caught like a flipped data byte.
 struct ShardFileHeader {
     char magic[4];  // "GEC1"
-    uint8_t k, m, index, reserved;
+    uint8_t k, m, index, sum_kind;
     uint32_t block_len;
     uint32_t shard_len;
     uint8_t sum[32];
-    uint8_t pad[16];
+    uint32_t hdr_check;  // Adler-32 of bytes [0, 48)
+    uint8_t pad[12];
 };
 static_assert(sizeof(ShardFileHeader) == 64, "shard file header is 64 bytes");
 
@@ -85,10 +112,13 @@ std::string hex_of(const uint8_t *p, size_t n)
     return o;
 }
 
+enum ReadResult { kReadOk = 0, kReadMissing = 1, kReadInvalid = 2 };
+
 struct Node {
     std::mutex mu;  // stands in for the 256 hash-sharded mutexes (manager.rs:114,679-689)
     bool up = true;
-    std::string dir;  // empty: in-memory store
+    bool fsync_data = false;  // data_fsync (util/config.rs), manager.rs:775-789
+    std::string dir;          // empty: in-memory store
     int k = 0, m = 0;
     std::unordered_map<Hash, StoredShard, HashHasher> shards;     // in-memory mode
     std::unordered_map<Hash, StoredShard, HashHasher> corrupted;  // the ".corrupted" quarantine
@@ -99,35 +129,85 @@ struct Node {
     {
         return dir + "/" + hex_of(h.data(), 1) + "/" + hex_of(h.data() + 1, 1) + "/" + hex_of(h.data(), 32) + ext;
     }
-    // all four are called with `mu` held
-    bool store_put(const Hash &h, StoredShard &&s)
+    bool meta_valid(const ShardMeta &mt) const
+    {
+        if (mt.index < 0 || mt.index >= k + m) return false;
+        return mt.shard_len == (uint32_t)(((uint64_t)mt.block_len + (unsigned)k - 1) / (unsigned)k);
+    }
+    // all store_* are called with `mu` held
+    bool store_put(const Hash &h, const ShardMeta &mt, const uint8_t *bytes, size_t n)
     {
         if (dir.empty()) {
-            shards[h] = std::move(s);
+            StoredShard &s = shards[h];
+            static_cast<ShardMeta &>(s) = mt;
+            s.bytes.assign(bytes, bytes + n);
             return true;
         }
         std::error_code ec;
-        std::filesystem::create_directories(dir + "/" + hex_of(h.data(), 1) + "/" + hex_of(h.data() + 1, 1), ec);
+        const std::string sub = dir + "/" + hex_of(h.data(), 1) + "/" + hex_of(h.data() + 1, 1);
+        std::filesystem::create_directories(sub, ec);
         const std::string fin = path_of(h, ".shard"), tmp = fin + ".tmp" + std::to_string((unsigned long)::getpid());
         ShardFileHeader hd;
         memset(&hd, 0, sizeof(hd));
         memcpy(hd.magic, "GEC1", 4);
         hd.k = (uint8_t)k;
         hd.m = (uint8_t)m;
-        hd.index = (uint8_t)s.index;
-        hd.block_len = s.block_len;
-        hd.shard_len = (uint32_t)s.bytes.size();
-        memcpy(hd.sum, s.sum.data(), 32);
+        hd.index = (uint8_t)mt.index;
+        hd.sum_kind = mt.sum_kind;
+        hd.block_len = mt.block_len;
+        hd.shard_len = (uint32_t)n;
+        memcpy(hd.sum, mt.sum.data(), 32);
+        hd.hdr_check = adler32_small(reinterpret_cast<const uint8_t *>(&hd), 48);
         FILE *f = fopen(tmp.c_str(), "wb");
         if (!f) return false;
-        bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 &&
-                  (s.bytes.empty() || fwrite(s.bytes.data(), s.bytes.size(), 1, f) == 1);
+        bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && (n == 0 || fwrite(bytes, n, 1, f) == 1);
+        if (ok) ok = fflush(f) == 0;
+        if (ok && fsync_data) ok = ::fsync(fileno(f)) == 0;  // manager.rs:775-777
         ok = (fclose(f) == 0) && ok;
         if (ok) ok = ::rename(tmp.c_str(), fin.c_str()) == 0;  // atomic publish (manager.rs:790-795)
+        if (ok && fsync_data) {                                 // and the directory entry (manager.rs:797-803)
+            const int dfd = ::open(sub.c_str(), O_RDONLY | O_DIRECTORY);
+            if (dfd >= 0) {
+                ok = ::fsync(dfd) == 0;
+                ::close(dfd);
+            }
+        }
         if (!ok) ::remove(tmp.c_str());
         return ok;
     }
-    bool store_get(const Hash &h, StoredShard &out) const
+    // shard bytes straight into `dst` (cap bytes available), metadata into `mt`
+    ReadResult store_read_into(const Hash &h, uint8_t *dst, size_t cap, ShardMeta &mt) const
+    {
+        if (dir.empty()) {
+            auto it = shards.find(h);
+            if (it == shards.end()) return kReadMissing;
+            mt = it->second;
+            if (!meta_valid(mt) || it->second.bytes.size() != mt.shard_len || mt.shard_len > cap) return kReadInvalid;
+            if (mt.shard_len) memcpy(dst, it->second.bytes.data(), mt.shard_len);
+            return kReadOk;
+        }
+        FILE *f = fopen(path_of(h, ".shard").c_str(), "rb");  // find_block (manager.rs:627-662)
+        if (!f) return kReadMissing;
+        ShardFileHeader hd;
+        ReadResult r = kReadInvalid;
+        struct stat sb;
+        // a header that fails any of these is a corrupt shard, never a reason to allocate or read
+        // what it claims (a flipped shard_len must not become a 4 GiB resize)
+        if (fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "GEC1", 4) == 0 &&
+            hd.hdr_check == adler32_small(reinterpret_cast<const uint8_t *>(&hd), 48) && hd.k == k && hd.m == m &&
+            fstat(fileno(f), &sb) == 0 && (uint64_t)sb.st_size == (uint64_t)hd.shard_len + sizeof(hd)) {
+            mt.index = hd.index;
+            mt.block_len = hd.block_len;
+            mt.shard_len = hd.shard_len;
+            mt.sum_kind = hd.sum_kind;
+            memcpy(mt.sum.data(), hd.sum, 32);
+            if (meta_valid(mt) && mt.shard_len <= cap && (mt.shard_len == 0 || fread(dst, mt.shard_len, 1, f) == 1))
+                r = kReadOk;
+        }
+        fclose(f);
+        return r;
+    }
+    bool store_get(const Hash &h, StoredShard &out) const  // a copy (scrub snapshots, inspection)
     {
         if (dir.empty()) {
             auto it = shards.find(h);
@@ -135,19 +215,14 @@ struct Node {
             out = it->second;
             return true;
         }
-        FILE *f = fopen(path_of(h, ".shard").c_str(), "rb");  // find_block (manager.rs:627-662)
-        if (!f) return false;
-        ShardFileHeader hd;
-        bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, "GEC1", 4) == 0;
-        if (ok) {
-            out.index = hd.index;
-            out.block_len = hd.block_len;
-            memcpy(out.sum.data(), hd.sum, 32);
-            out.bytes.resize(hd.shard_len);
-            ok = hd.shard_len == 0 || fread(out.bytes.data(), hd.shard_len, 1, f) == 1;
-        }
-        fclose(f);
-        return ok;
+        std::error_code ec;
+        const auto sz = std::filesystem::file_size(path_of(h, ".shard"), ec);
+        if (ec || sz < sizeof(ShardFileHeader) || sz > (1ull << 31)) return false;
+        out.bytes.resize((size_t)sz - sizeof(ShardFileHeader));
+        ShardMeta mt;
+        if (store_read_into(h, out.bytes.data(), out.bytes.size(), mt) != kReadOk) return false;
+        static_cast<ShardMeta &>(out) = mt;
+        return true;
     }
     bool store_has(const Hash &h) const
     {
@@ -230,11 +305,15 @@ class Batcher {
 public:
     using Run = std::function<void(int /*worker*/, std::vector<Item *> &)>;
     // `workers` dispatcher threads pull batches from one queue: while one batch is on the GPU the
-    // next one is being collected / copied (each worker owns a garage_ec context and buffers)
-    Batcher(size_t max_items, unsigned linger_us, int workers, Run run)
+    // next one is being collected (each worker owns a garage_ec context and buffers)
+    Batcher(size_t max_items, unsigned linger_us, int workers, Run run, std::function<void()> on_thread_start)
         : max_(std::max<size_t>(1, max_items)), linger_(linger_us), run_(std::move(run))
     {
-        for (int w = 0; w < std::max(1, workers); w++) th_.emplace_back([this, w] { loop(w); });
+        for (int w = 0; w < std::max(1, workers); w++)
+            th_.emplace_back([this, w, on_thread_start] {
+                if (on_thread_start) on_thread_start();
+                loop(w);
+            });
     }
     ~Batcher()
     {
@@ -270,7 +349,7 @@ private:
                 cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
                 if (stop_ && q_.empty()) return;
                 // linger: give concurrent callers a moment to join the batch
-                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(linger_);
+                const auto deadline = Clock::now() + std::chrono::microseconds(linger_);
                 while (q_.size() < max_ && !stop_) {
                     if (cv_.wait_until(lk, deadline) == std::cv_status::timeout) break;
                 }
@@ -282,7 +361,17 @@ private:
             if (batch.empty()) continue;  // another worker took them
             batches_++;
             items_ += batch.size();
-            run_(w, batch);  // sets every item's promise
+            // nothing may escape a dispatcher thread: an exception (bad_alloc in a staging vector)
+            // fails the items of this batch instead of terminating the process
+            try {
+                run_(w, batch);  // sets every item's promise
+            } catch (...) {
+                for (Item *it : batch)
+                    if (!it->fulfilled) {
+                        it->fulfilled = true;
+                        it->done.set_value(GARAGE_EC_E_NOMEM);
+                    }
+            }
         }
     }
     const size_t max_;
@@ -296,17 +385,17 @@ private:
     std::vector<std::thread> th_;
 };
 
-// pool of pinned block-sized slots: the calling thread copies its block into a slot (in
-// parallel with every other caller) so the dispatcher's H2D runs at PCIe speed from pinned
-// memory -- in Garage proper the body copy of BytesBuf::take_exact would land here directly
+// pool of pinned slots: the calling thread fills its slot (in parallel with every other caller)
+// so the dispatcher's DMA runs at PCIe speed from pinned, NUMA-local memory -- in Garage proper
+// the body copy of BytesBuf::take_exact (src/net/bytes_buf.rs:66-117) would land here directly
 class SlotPool {
 public:
     bool init(garage_ec_ctx *ctx, size_t slots, size_t slot_bytes)
     {
         ctx_ = ctx;
-        slot_bytes_ = slot_bytes;
-        if (garage_ec_host_alloc(ctx, &base_, slots * slot_bytes) != GARAGE_EC_OK) return false;
-        for (size_t i = 0; i < slots; i++) free_.push_back(static_cast<uint8_t *>(base_) + i * slot_bytes);
+        slot_bytes_ = (slot_bytes + 4095) / 4096 * 4096;
+        if (garage_ec_host_alloc(ctx, &base_, slots * slot_bytes_) != GARAGE_EC_OK) return false;
+        for (size_t i = 0; i < slots; i++) free_.push_back(static_cast<uint8_t *>(base_) + i * slot_bytes_);
         return true;
     }
     uint8_t *acquire()
@@ -340,24 +429,86 @@ private:
     std::condition_variable cv_;
     std::vector<uint8_t *> free_;
 };
+struct SlotLease {  // RAII: a slot goes back to its pool on every path
+    SlotPool &pool;
+    uint8_t *p;
+    explicit SlotLease(SlotPool &pl) : pool(pl), p(pl.acquire()) {}
+    ~SlotLease() { pool.release(p); }
+    SlotLease(const SlotLease &) = delete;
+    SlotLease &operator=(const SlotLease &) = delete;
+};
+
+// pinned output buffer of one encode batch (parity rows + shard tags).  The callers of the batch
+// store their shards straight out of it; the dispatcher reuses it only when they are all done.
+struct EncBatchBuf {
+    garage_ec_ctx *ctx = nullptr;
+    void *p = nullptr;
+    size_t cap = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int pending = 0;
+    uint8_t *get(size_t n)
+    {
+        if (n > cap) {
+            if (p) garage_ec_host_free(ctx, p);
+            p = nullptr;
+            cap = 0;
+            const size_t want = std::max(n, (size_t)1 << 20);
+            if (garage_ec_host_alloc(ctx, &p, want) != GARAGE_EC_OK) return nullptr;
+            cap = want;
+        }
+        return static_cast<uint8_t *>(p);
+    }
+    void wait_idle()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return pending == 0; });
+    }
+    void set_pending(int n)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        pending = n;
+    }
+    void done_one()
+    {
+        bool zero;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            zero = --pending == 0;
+        }
+        if (zero) cv.notify_all();
+    }
+    void release()
+    {
+        if (p) garage_ec_host_free(ctx, p);
+        p = nullptr;
+        cap = 0;
+    }
+};
 
 struct EncodeItem {
-    const uint8_t *data = nullptr;
+    const uint8_t *data = nullptr;  // the block (pinned slot, or the caller's buffer for oversize blocks)
     uint32_t len = 0;
-    std::vector<uint8_t> parity;  // m * shard_len bytes, row i at i * shard_len
-    std::vector<Hash> sums;       // k+m
+    // filled by the dispatcher: parity row i at parity + i * pstride, tags of the k+m shards
+    const uint8_t *parity = nullptr;
+    size_t pstride = 0;
+    const uint8_t *sums = nullptr;
+    EncBatchBuf *buf = nullptr;  // to be released (done_one) once the shards are stored
+    bool fulfilled = false;
     std::promise<int> done;
 };
 
 struct ReconItem {
+    uint8_t *stripe = nullptr;  // pinned slot: k+m shards, `stride` apart, survivors filled in by the caller
+    size_t stride = 0;
     uint32_t block_len = 0;
-    std::vector<const uint8_t *> shard;          // k+m pointers, nullptr = absent
-    std::vector<uint8_t> want;                   // k+m
-    std::vector<std::vector<uint8_t>> rebuilt;   // k+m, filled for wanted absent shards
+    uint8_t present[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
+    uint8_t want[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
+    bool fulfilled = false;
     std::promise<int> done;
 };
 
-// pinned scratch that grows on demand (owned by one dispatcher thread)
+// pinned scratch that grows on demand (owned by one thread at a time)
 struct PinnedBuf {
     garage_ec_ctx *ctx = nullptr;
     void *p = nullptr;
@@ -382,34 +533,46 @@ struct PinnedBuf {
     ~PinnedBuf() { release(); }
 };
 
+struct RcEntry {
+    int64_t count = 0;
+    Clock::time_point zero_since{};  // when the count last dropped to 0 (BLOCK_GC_DELAY, manager.rs:49-52)
+};
+
 }  // namespace
 
 // ================================================================= the manager
 struct garage_bm {
     garage_bm_config cfg{};
     int k = 0, m = 0, tot = 0;
-    static constexpr int kWorkers = 3;  // dispatcher threads per batcher (overlap PCIe / GPU / CPU copies)
-    garage_ec_ctx *ec = nullptr;                 // scrub + geometry helpers
-    garage_ec_ctx *enc_ctx[kWorkers] = {nullptr};  // one context (= one set of staging lanes) per worker
+    int sum_kind = GARAGE_EC_SUM_ADLER8;
+    size_t slot_stride = 0;  // stride of the largest block's shards: geometry of every stripe slot
+    static constexpr int kWorkers = 3;  // dispatcher threads per batcher (overlap PCIe / GPU / collection)
+    garage_ec_ctx *ec = nullptr;                   // scrub + geometry helpers
+    garage_ec_ctx *enc_ctx[kWorkers] = {nullptr};  // one context (= its own staging lanes) per worker
     garage_ec_ctx *rec_ctx[kWorkers] = {nullptr};
-    SlotPool slots;
+    SlotPool put_slots;     // one block each
+    SlotPool stripe_slots;  // (k+m) x slot_stride each: degraded GETs, resync workers
     std::vector<std::unique_ptr<Node>> nodes;
     // stands in for the block_ref / rc tables (src/model/s3/block_ref_table.rs, src/block/rc.rs):
-    // which blocks exist and how long they are
+    // which blocks exist and how long they are.  Lock order: refs_mu before any Node::mu.
     std::mutex refs_mu;
     std::unordered_map<Hash, uint32_t, HashHasher> refs;
     // block reference counts (src/block/rc.rs): only blocks that went through block_incref /
     // block_decref have an entry; a block without entry is treated as needed (rc > 0)
-    std::unordered_map<Hash, int64_t, HashHasher> rc;
+    std::unordered_map<Hash, RcEntry, HashHasher> rc;
     std::unique_ptr<ByteSemaphore> ram;
     std::unique_ptr<Batcher<EncodeItem>> enc_batcher;
     std::unique_ptr<Batcher<ReconItem>> rec_batcher;
-    PinnedBuf enc_parity[kWorkers], rec_buf[kWorkers], scrub_buf;
+    EncBatchBuf enc_out[kWorkers][2];
+    int enc_next[kWorkers] = {0};
+    PinnedBuf scrub_buf;
     std::mutex scrub_mu;
     // metrics (src/block/metrics.rs)
     std::atomic<uint64_t> bytes_written{0}, bytes_read{0}, corruption_counter{0}, resync_counter{0},
         resync_error_counter{0}, resync_recv_counter{0}, delete_counter{0}, put_calls{0}, reconstruct_calls{0},
-        scrub_checked{0}, scrub_corrupt{0}, enc_gpu_us{0}, rec_gpu_us{0};
+        scrub_checked{0}, scrub_corrupt{0}, enc_gpu_us{0}, rec_gpu_us{0}, corrupt_data_errors{0}, write_errors{0};
+
+    size_t shard_len_of(uint32_t block_len) const { return garage_ec_shard_len(block_len, k); }
 
     // rpc/layout/version.rs:117-137: top 8 bits of the hash -> partition -> k+m distinct nodes
     void storage_nodes_of(const Hash &h, int *out) const
@@ -426,41 +589,63 @@ struct garage_bm {
         if (nd.queued.insert(h).second) nd.resync_queue.push_back(h);
     }
 
-    // manager.rs:517-530 write_block
-    void write_shard(int node, const Hash &h, int index, uint32_t block_len, const uint8_t *bytes, size_t n,
-                     const Hash &sum)
+    void shard_tag(const uint8_t *bytes, size_t n, Hash &out) const
     {
-        StoredShard s;
-        s.index = index;
-        s.block_len = block_len;
-        s.bytes.assign(bytes, bytes + n);
-        s.sum = sum;
-        Node &nd = *nodes[node];
-        std::lock_guard<std::mutex> lk(nd.mu);
-        nd.store_put(h, std::move(s));
-        bytes_written += n;
+        garage_ec_shard_sum_host(sum_kind, bytes, n, out.data());
     }
 
-    // manager.rs:554-609 read_block + read_block_from: returns a COPY of the verified shard, or false.
-    // A checksum mismatch quarantines the shard and queues a resync, like the reference.
-    bool read_shard(int node, const Hash &h, StoredShard &out)
+    // manager.rs:517-530 write_block: false if the node is down or the store failed (ENOSPC, EACCES ...)
+    bool write_shard(int node, const Hash &h, int index, uint32_t block_len, const uint8_t *bytes, size_t n,
+                     const uint8_t *sum32)
     {
+        ShardMeta mt;
+        mt.index = index;
+        mt.block_len = block_len;
+        mt.shard_len = (uint32_t)n;
+        mt.sum_kind = (uint8_t)sum_kind;
+        memcpy(mt.sum.data(), sum32, 32);
         Node &nd = *nodes[node];
+        bool ok;
         {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return false;
-            if (!nd.store_get(h, out)) return false;
+            ok = nd.store_put(h, mt, bytes, n);
         }
-        bytes_read += out.bytes.size();
-        Hash got;
-        garage_ec_blake2sum(out.bytes.data(), out.bytes.size(), got.data());
-        if (got == out.sum) return true;
+        if (ok) bytes_written += n;
+        else write_errors++;
+        return ok;
+    }
+
+    void quarantine(int node, const Hash &h)
+    {
         corruption_counter++;
         {
+            Node &nd = *nodes[node];
             std::lock_guard<std::mutex> lk(nd.mu);
             nd.store_quarantine(h);
         }
         put_to_resync(node, h);
+    }
+
+    // manager.rs:554-609 read_block + read_block_from: the verified shard bytes land in `dst`.
+    // A bad header or a tag mismatch quarantines the shard and queues a resync, like the reference.
+    bool read_shard_into(int node, const Hash &h, uint8_t *dst, size_t cap, ShardMeta &mt)
+    {
+        Node &nd = *nodes[node];
+        ReadResult r;
+        {
+            std::lock_guard<std::mutex> lk(nd.mu);
+            if (!nd.up) return false;
+            r = nd.store_read_into(h, dst, cap, mt);
+        }
+        if (r == kReadMissing) return false;
+        if (r == kReadOk) {
+            bytes_read += mt.shard_len;
+            Hash got;
+            if (garage_ec_shard_sum_host(mt.sum_kind, dst, mt.shard_len, got.data()) == GARAGE_EC_OK && got == mt.sum)
+                return true;
+        }
+        quarantine(node, h);
         return false;
     }
 
@@ -477,21 +662,24 @@ struct garage_bm {
             max_len = std::max(max_len, b[i]->len);
         }
         const size_t stride = garage_ec_stride_for(garage_ec_shard_len(max_len, k));
-        uint8_t *par = enc_parity[w].get(n * m * stride + n * tot * 32);
+        EncBatchBuf &bb = enc_out[w][enc_next[w] ^= 1];
+        bb.wait_idle();  // the callers of the batch before last have stored their shards
+        uint8_t *par = bb.get(n * m * stride + n * tot * 32);
         int rc = par ? GARAGE_EC_OK : GARAGE_EC_E_NOMEM;
         uint8_t *sums = par ? par + n * m * stride : nullptr;
-        const auto t0 = std::chrono::steady_clock::now();
+        const auto t0 = Clock::now();
         if (rc == GARAGE_EC_OK)
             rc = garage_ec_encode_blocks_with_sums(enc_ctx[w], ptrs.data(), lens.data(), n, par, sums, stride);
-        enc_gpu_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        enc_gpu_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - t0).count();
+        if (rc == GARAGE_EC_OK) bb.set_pending((int)n);
         for (size_t i = 0; i < n; i++) {
             if (rc == GARAGE_EC_OK) {
-                const size_t L = garage_ec_shard_len(lens[i], k);
-                b[i]->parity.resize((size_t)m * L);
-                for (int r = 0; r < m; r++) memcpy(b[i]->parity.data() + r * L, par + (i * m + r) * stride, L);
-                b[i]->sums.resize(tot);
-                for (int s = 0; s < tot; s++) memcpy(b[i]->sums[s].data(), sums + (i * tot + s) * 32, 32);
+                b[i]->parity = par + i * m * stride;
+                b[i]->pstride = stride;
+                b[i]->sums = sums + i * tot * 32;
+                b[i]->buf = &bb;
             }
+            b[i]->fulfilled = true;
             b[i]->done.set_value(rc);
         }
     }
@@ -499,121 +687,148 @@ struct garage_bm {
     void run_reconstruct(int w, std::vector<ReconItem *> &b)
     {
         const size_t n = b.size();
-        uint32_t max_len = 0;
-        for (auto *it : b) max_len = std::max(max_len, it->block_len);
-        const size_t stride = garage_ec_stride_for(garage_ec_shard_len(max_len, k));
-        const size_t data_b = n * tot * stride;
-        uint8_t *buf = rec_buf[w].get(data_b + 2 * n * tot + n * 8);
-        if (!buf) {
-            for (auto *it : b) it->done.set_value(GARAGE_EC_E_NOMEM);
-            return;
-        }
-        uint8_t *present = buf + data_b, *want = present + n * tot;
+        std::vector<uint8_t *> stripes(n);
+        std::vector<uint8_t> present(n * tot), want(n * tot);
         std::vector<uint32_t> lens(n);
         std::vector<int32_t> status(n, 0);
         for (size_t i = 0; i < n; i++) {
-            const size_t L = garage_ec_shard_len(b[i]->block_len, k);
-            lens[i] = (uint32_t)L;
-            for (int s = 0; s < tot; s++) {
-                present[i * tot + s] = b[i]->shard[s] ? 1 : 0;
-                want[i * tot + s] = b[i]->want[s];
-                if (b[i]->shard[s]) memcpy(buf + (i * tot + s) * stride, b[i]->shard[s], L);
-            }
+            stripes[i] = b[i]->stripe;
+            lens[i] = (uint32_t)shard_len_of(b[i]->block_len);
+            memcpy(present.data() + i * tot, b[i]->present, tot);
+            memcpy(want.data() + i * tot, b[i]->want, tot);
         }
-        const auto t0 = std::chrono::steady_clock::now();
-        int rc = garage_ec_reconstruct(rec_ctx[w], buf, present, want, status.data(), lens.data(), stride, n,
-                                       GARAGE_EC_MEM_HOST, nullptr);
-        rec_gpu_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        const auto t0 = Clock::now();
+        int rc = garage_ec_reconstruct_stripes(rec_ctx[w], stripes.data(), present.data(), want.data(), status.data(),
+                                               lens.data(), slot_stride, n);
+        rec_gpu_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - t0).count();
         for (size_t i = 0; i < n; i++) {
             int r = rc;
-            if (rc == GARAGE_EC_OK || rc == GARAGE_EC_E_UNRECOVERABLE) {
-                r = status[i] ? GARAGE_BM_E_MISSING_BLOCK : GARAGE_BM_OK;
-                if (r == GARAGE_BM_OK) {
-                    b[i]->rebuilt.assign(tot, {});
-                    for (int s = 0; s < tot; s++)
-                        if (!b[i]->shard[s] && b[i]->want[s])
-                            b[i]->rebuilt[s].assign(buf + (i * tot + s) * stride, buf + (i * tot + s) * stride + lens[i]);
-                }
-            }
+            if (rc == GARAGE_EC_OK || rc == GARAGE_EC_E_UNRECOVERABLE) r = status[i] ? GARAGE_BM_E_MISSING_BLOCK : GARAGE_BM_OK;
+            b[i]->fulfilled = true;
             b[i]->done.set_value(r);
         }
     }
 
-    // gather the valid shards of `h` from every up node except `skip_node`
-    int gather(const Hash &h, int skip_node, std::vector<StoredShard> &got, std::vector<uint8_t> &have,
-               uint32_t &block_len)
+    // Read the valid shards of `h` from every up node except `skip_node` into the stripe slot
+    // (shard i at slot + i*slot_stride).  Data shards first (a complete set needs no GPU), then only
+    // as many parity shards as it takes to reach k -- the reference likewise stops at the first good
+    // copy (manager.rs:292-334); RpcHelper::try_call_many with quorum k is the real-cluster form.
+    // A shard whose header disagrees with the others on the block length, or that sits under the
+    // wrong index, is treated like a corrupt one.  `all`: do not stop at k (corruption hunting).
+    int gather_into(const Hash &h, int skip_node, uint8_t *slot, uint8_t *have, uint32_t &block_len, bool all = false)
     {
         int who[64];
         storage_nodes_of(h, who);
-        got.assign(tot, {});
-        have.assign(tot, 0);
+        memset(have, 0, tot);
+        uint32_t expect = 0;
+        bool have_expect = false;
+        {
+            std::lock_guard<std::mutex> lk(refs_mu);
+            auto it = refs.find(h);
+            if (it != refs.end()) {
+                expect = it->second;
+                have_expect = true;
+            }
+        }
         int count = 0;
         auto try_shard = [&](int i) {
             if (who[i] == skip_node || have[i]) return;
-            StoredShard s;
-            if (read_shard(who[i], h, s) && s.index == i) {
-                block_len = s.block_len;
-                got[i] = std::move(s);
-                have[i] = 1;
-                count++;
+            ShardMeta mt;
+            if (!read_shard_into(who[i], h, slot + (size_t)i * slot_stride, slot_stride, mt)) return;
+            if (mt.index != i || (have_expect && mt.block_len != expect)) {
+                quarantine(who[i], h);  // a stale or misplaced shard with a self-consistent tag
+                return;
             }
+            if (!have_expect) {
+                expect = mt.block_len;
+                have_expect = true;
+            }
+            have[i] = 1;
+            count++;
         };
-        // data shards first (a complete set needs no GPU), then only as many parity shards as
-        // it takes to reach k -- the reference likewise stops at the first good copy
-        // (manager.rs:292-334); RpcHelper::try_call_many with quorum k is the real-cluster form
         for (int i = 0; i < k; i++) try_shard(i);
-        for (int i = k; i < tot && count < k; i++) try_shard(i);
+        for (int i = k; i < tot && (all || count < k); i++) try_shard(i);
+        block_len = expect;
         return count;
+    }
+
+    int reconstruct_in_slot(uint8_t *slot, uint32_t block_len, const uint8_t *have, const uint8_t *want)
+    {
+        reconstruct_calls++;
+        ReconItem it;
+        it.stripe = slot;
+        it.stride = slot_stride;
+        it.block_len = block_len;
+        memcpy(it.present, have, tot);
+        memcpy(it.want, want, tot);
+        return rec_batcher->submit(it);
+    }
+
+    void assemble(const uint8_t *slot, uint32_t block_len, uint8_t *out) const
+    {
+        const size_t L = shard_len_of(block_len);
+        for (int j = 0; j < k; j++) {
+            const size_t off = (size_t)j * L;
+            if (off >= block_len) break;
+            memcpy(out + off, slot + (size_t)j * slot_stride, std::min(L, (size_t)block_len - off));
+        }
+    }
+
+    bool content_ok(const Hash &h, const uint8_t *data, size_t len) const
+    {
+        if (!cfg.verify_content_hash) return true;
+        Hash got;
+        garage_ec_blake2sum(data, len, got.data());  // DataBlock::verify, src/block/block.rs:69-83
+        return got == h;
     }
 
     int rpc_put_block(const Hash &h, const uint8_t *data, size_t len)
     {
-        if (len == 0 || len > 0xffffffffull) return GARAGE_BM_E_MESSAGE;
+        if (len == 0 || len > cfg.block_size) return GARAGE_BM_E_MESSAGE;  // blocks are at most block_size (put.rs:583-617)
         int who[64];
         storage_nodes_of(h, who);  // manager.rs:373
         // DataBlock::from_buffer (manager.rs:376): compression is 'none' in this mirror
         const uint64_t permits = (uint64_t)len * tot / k;  // manager.rs:380-385, x (k+m)/k for the parity
         ram->acquire(permits);
+        struct Permit {
+            ByteSemaphore &s;
+            uint64_t n;
+            ~Permit() { s.release(n); }
+        } permit{*ram, permits};
         put_calls++;
         // land the block in pinned memory (caller's thread, so copies of concurrent PUTs overlap)
-        uint8_t *slot = len <= slots.slot_bytes() ? slots.acquire() : nullptr;
-        if (slot) memcpy(slot, data, len);
+        SlotLease slot(put_slots);
+        memcpy(slot.p, data, len);
         EncodeItem it;
-        it.data = slot ? slot : data;
+        it.data = slot.p;
         it.len = (uint32_t)len;
         int rc = enc_batcher->submit(it);
-        if (slot) slots.release(slot);
-        if (rc != GARAGE_EC_OK) {
-            ram->release(permits);
-            return rc;
-        }
-        const size_t L = garage_ec_shard_len((uint32_t)len, k);
-        std::vector<uint8_t> pad(L);
+        if (rc != GARAGE_EC_OK) return rc;
+        struct BufRelease {
+            EncBatchBuf *b;
+            ~BufRelease() { b->done_one(); }
+        } rel{it.buf};
+        const size_t L = shard_len_of((uint32_t)len);
+        std::vector<uint8_t> pad;
         int stored = 0;
         for (int i = 0; i < tot; i++) {  // try_write_many_sets (manager.rs:395-405): all at once
-            Node &nd = *nodes[who[i]];
-            {
-                std::lock_guard<std::mutex> lk(nd.mu);
-                if (!nd.up) continue;
-            }
             const uint8_t *src;
             if (i < k) {
                 const size_t off = (size_t)i * L;
                 const size_t have = off < len ? std::min(L, len - off) : 0;
                 if (have == L) {
-                    src = data + off;
+                    src = slot.p + off;
                 } else {  // zero padded tail shard (put.rs:611-615 short last block)
-                    std::fill(pad.begin(), pad.end(), 0);
-                    if (have) memcpy(pad.data(), data + off, have);
+                    pad.assign(L, 0);
+                    if (have) memcpy(pad.data(), slot.p + off, have);
                     src = pad.data();
                 }
             } else {
-                src = it.parity.data() + (size_t)(i - k) * L;
+                src = it.parity + (size_t)(i - k) * it.pstride;
             }
-            write_shard(who[i], h, i, (uint32_t)len, src, L, it.sums[i]);
-            stored++;
+            // only a shard that is durably stored counts towards the quorum
+            if (write_shard(who[i], h, i, (uint32_t)len, src, L, it.sums + (size_t)i * 32)) stored++;
         }
-        ram->release(permits);
         {
             std::lock_guard<std::mutex> lk(refs_mu);
             refs[h] = (uint32_t)len;
@@ -622,39 +837,64 @@ struct garage_bm {
         return stored >= quorum ? GARAGE_BM_OK : GARAGE_BM_E_QUORUM;
     }
 
-    int rpc_get_block(const Hash &h, std::vector<uint8_t> &out)
+    // manager.rs:344-363 + 276-339.  `out` must hold block_size bytes; *out_len = the block's length.
+    int rpc_get_block(const Hash &h, uint8_t *out, size_t cap, size_t *out_len)
     {
-        std::vector<StoredShard> got;
-        std::vector<uint8_t> have;
+        SlotLease slot(stripe_slots);
+        uint8_t have[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M], want[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
         uint32_t block_len = 0;
-        const int count = gather(h, -1, got, have, block_len);
+        const int count = gather_into(h, -1, slot.p, have, block_len);
         if (count < k) return GARAGE_BM_E_MISSING_BLOCK;  // manager.rs:336-338
-        const size_t L = garage_ec_shard_len(block_len, k);
+        *out_len = block_len;
+        if (block_len > cap) return GARAGE_EC_E_INVALID;
         bool all_data = true;
-        for (int j = 0; j < k; j++) all_data &= have[j] != 0;
-        std::vector<std::vector<uint8_t>> rebuilt;
-        if (!all_data) {
-            reconstruct_calls++;
-            ReconItem it;
-            it.block_len = block_len;
-            it.shard.assign(tot, nullptr);
-            it.want.assign(tot, 0);
-            for (int i = 0; i < tot; i++) {
-                if (have[i]) it.shard[i] = got[i].bytes.data();
-                else if (i < k) it.want[i] = 1;
-            }
-            int rc = rec_batcher->submit(it);
-            if (rc != GARAGE_BM_OK) return rc;
-            rebuilt = std::move(it.rebuilt);
-        }
-        out.resize(block_len);
         for (int j = 0; j < k; j++) {
-            const size_t off = (size_t)j * L;
-            if (off >= block_len) break;
-            const size_t n = std::min(L, (size_t)block_len - off);
-            memcpy(out.data() + off, have[j] ? got[j].bytes.data() : rebuilt[j].data(), n);
+            all_data &= have[j] != 0;
+            want[j] = !have[j];
         }
-        return GARAGE_BM_OK;
+        if (!all_data) {
+            int rc = reconstruct_in_slot(slot.p, block_len, have, want);
+            if (rc != GARAGE_BM_OK) return rc;
+        }
+        assemble(slot.p, block_len, out);
+        if (content_ok(h, out, block_len)) return GARAGE_BM_OK;
+        // Every shard passed its own tag, yet the block is not the one `h` names: some shard is
+        // stale or was rebuilt wrongly.  Find it: gather everything, drop one shard at a time,
+        // rebuild, re-check (manager.rs read path: CorruptData -> quarantine + resync).
+        corrupt_data_errors++;
+        const int avail = gather_into(h, -1, slot.p, have, block_len, /*all=*/true);
+        if (avail > k && block_len <= cap) {
+            int who[64];
+            storage_nodes_of(h, who);
+            SlotLease trial(stripe_slots);
+            for (int x = 0; x < tot; x++) {
+                if (!have[x]) continue;
+                uint8_t h2[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M], w2[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
+                memcpy(h2, have, tot);
+                h2[x] = 0;
+                bool need = false;
+                for (int j = 0; j < k; j++) {
+                    w2[j] = !h2[j];
+                    need |= w2[j] != 0;
+                }
+                memcpy(trial.p, slot.p, (size_t)tot * slot_stride);
+                if (need && reconstruct_in_slot(trial.p, block_len, h2, w2) != GARAGE_BM_OK) continue;
+                assemble(trial.p, block_len, out);
+                if (content_ok(h, out, block_len)) {
+                    quarantine(who[x], h);  // the culprit
+                    *out_len = block_len;
+                    return GARAGE_BM_OK;
+                }
+            }
+        }
+        return GARAGE_BM_E_CORRUPT_DATA;
+    }
+
+    bool deletable_now(const Hash &h)  // refs_mu held.  rc.is_deletable() + BLOCK_GC_DELAY (rc.rs, manager.rs:49-52)
+    {
+        auto it = rc.find(h);
+        if (it == rc.end() || it->second.count > 0) return false;
+        return Clock::now() - it->second.zero_since >= std::chrono::milliseconds(cfg.block_gc_delay_ms);
     }
 
     int resync_block(int node, const Hash &h)
@@ -665,50 +905,52 @@ struct garage_bm {
         for (int i = 0; i < tot; i++)
             if (who[i] == node) idx = i;
         if (idx < 0) return GARAGE_BM_OK;  // not a storage node for it any more (resync.rs:466-477)
-        bool known, deletable;
+        bool known, unneeded;
         {
-            std::lock_guard<std::mutex> lk(refs_mu);
+            // the deletion decision and the deletion itself happen under BOTH locks (refs_mu, then the
+            // node's): an incref / re-PUT cannot slip in between the check and the erase
+            std::lock_guard<std::mutex> rl(refs_mu);
             known = refs.count(h) != 0;
             auto it = rc.find(h);
-            deletable = it != rc.end() && it->second <= 0;  // rc.is_deletable() (rc.rs)
-        }
-        {
+            unneeded = it != rc.end() && it->second.count <= 0;
             Node &nd = *nodes[node];
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return GARAGE_BM_E_MESSAGE;
             const bool exists = nd.store_has(h);
-            if (exists && deletable) {  // offload branch, resync.rs:369-458: nobody needs it -> delete_if_unneeded
+            if (exists && unneeded) {  // offload branch, resync.rs:369-458: nobody needs it -> delete_if_unneeded
+                if (!deletable_now(h)) {  // still inside the GC delay: look again later
+                    if (nd.queued.insert(h).second) nd.resync_queue.push_back(h);
+                    return GARAGE_BM_OK;
+                }
                 if (nd.store_erase(h)) delete_counter++;
                 return GARAGE_BM_OK;
             }
             if (exists) return GARAGE_BM_OK;
         }
-        if (!known || deletable) return GARAGE_BM_OK;  // rc == 0: nothing to fetch
-        std::vector<StoredShard> got;
-        std::vector<uint8_t> have;
+        if (!known || unneeded) return GARAGE_BM_OK;  // rc == 0: nothing to fetch
+        SlotLease slot(stripe_slots);
+        uint8_t have[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M], want[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
         uint32_t block_len = 0;
-        const int count = gather(h, node, got, have, block_len);
+        const int count = gather_into(h, node, slot.p, have, block_len);
         if (count < k) {
             resync_error_counter++;
             return GARAGE_BM_E_MISSING_BLOCK;  // resync.rs:488-494
         }
-        reconstruct_calls++;
-        ReconItem it;
-        it.block_len = block_len;
-        it.shard.assign(tot, nullptr);
-        it.want.assign(tot, 0);
-        for (int i = 0; i < tot; i++)
-            if (have[i]) it.shard[i] = got[i].bytes.data();
-        it.want[idx] = 1;
-        int rc = rec_batcher->submit(it);
-        if (rc != GARAGE_BM_OK) {
+        want[idx] = 1;
+        int rc2 = reconstruct_in_slot(slot.p, block_len, have, want);
+        if (rc2 != GARAGE_BM_OK) {
             resync_error_counter++;
-            return rc;
+            return rc2;
         }
         resync_recv_counter++;
+        const size_t L = shard_len_of(block_len);
+        const uint8_t *bytes = slot.p + (size_t)idx * slot_stride;
         Hash sum;
-        garage_ec_blake2sum(it.rebuilt[idx].data(), it.rebuilt[idx].size(), sum.data());
-        write_shard(node, h, idx, block_len, it.rebuilt[idx].data(), it.rebuilt[idx].size(), sum);  // resync.rs:499
+        shard_tag(bytes, L, sum);
+        if (!write_shard(node, h, idx, block_len, bytes, L, sum.data())) {  // resync.rs:499
+            resync_error_counter++;
+            return GARAGE_BM_E_MESSAGE;  // Error::Io: stays queued, the caller backs off (resync.rs:300-315)
+        }
         resync_counter++;
         return GARAGE_BM_OK;
     }
@@ -716,15 +958,15 @@ struct garage_bm {
     // BlockManager::block_incref / block_decref (manager.rs:452-500), driven in Garage by
     // BlockRefTable::updated (src/model/s3/block_ref_table.rs:69-85): a 0 -> 1 transition queues a
     // resync on every storage node of the block (safety check that the shard really arrives), a
-    // drop to 0 queues one too (so that the shard gets deleted).
+    // drop to 0 queues one too (so that the shard gets deleted once BLOCK_GC_DELAY has passed).
     void block_incref(const Hash &h)
     {
         bool first;
         {
             std::lock_guard<std::mutex> lk(refs_mu);
-            int64_t &c = rc[h];
-            first = c <= 0;
-            c = first ? 1 : c + 1;
+            RcEntry &c = rc[h];
+            first = c.count <= 0;
+            c.count = first ? 1 : c.count + 1;
         }
         if (first) queue_on_storage_nodes(h);
     }
@@ -734,8 +976,9 @@ struct garage_bm {
         {
             std::lock_guard<std::mutex> lk(refs_mu);
             auto it = rc.find(h);
-            if (it == rc.end()) it = rc.emplace(h, 1).first;  // an un-counted block counts as referenced once
-            if (it->second > 0 && --it->second == 0) {
+            if (it == rc.end()) it = rc.emplace(h, RcEntry{1, {}}).first;  // an un-counted block counts as referenced once
+            if (it->second.count > 0 && --it->second.count == 0) {
+                it->second.zero_since = Clock::now();
                 zero = true;
                 refs.erase(h);
             }
@@ -752,7 +995,7 @@ struct garage_bm {
     {
         std::lock_guard<std::mutex> lk(refs_mu);
         auto it = rc.find(h);
-        return it == rc.end() ? -1 : it->second;
+        return it == rc.end() ? -1 : it->second.count;
     }
 
     int resync_all(int node, int workers, uint64_t *resynced)
@@ -773,10 +1016,17 @@ struct garage_bm {
         std::vector<std::thread> th;
         for (int w = 0; w < workers; w++)
             th.emplace_back([&] {
+                garage_ec_bind_thread(ec);
                 for (;;) {
                     const size_t i = next++;
                     if (i >= todo.size()) return;
-                    if (resync_block(node, todo[i]) == GARAGE_BM_OK) {
+                    int r;
+                    try {
+                        r = resync_block(node, todo[i]);
+                    } catch (...) {
+                        r = GARAGE_EC_E_NOMEM;
+                    }
+                    if (r == GARAGE_BM_OK) {
                         ok++;
                     } else {
                         std::lock_guard<std::mutex> lk(failed_mu);
@@ -818,7 +1068,7 @@ struct garage_bm {
         return GARAGE_BM_OK;
     }
 
-    // ScrubWorker sweep of one node (repair.rs:438-490) with the GPU doing the hashing
+    // ScrubWorker sweep of one node (repair.rs:438-490) with the GPU computing the shard tags
     // `cursor`/`max_shards`: the scrub iterator checkpoint of the reference (ScrubWorker persists
     // its BlockStoreIterator position every 60 s, repair.rs:186-193,460-464, so a sweep survives a
     // restart): shards are visited in hash order, starting after *cursor (NULL = from the start),
@@ -850,47 +1100,46 @@ struct garage_bm {
         }
         uint64_t nchecked = 0, nbad = 0;
         const size_t chunk = std::max<size_t>(1, (size_t)cfg.batch_max_blocks * tot);
+        const size_t stride = slot_stride;
         for (size_t c0 = 0; c0 < hashes.size(); c0 += chunk) {
             const size_t n = std::min(chunk, hashes.size() - c0);
-            std::vector<StoredShard> snap(n);
-            std::vector<uint8_t> ok(n, 0);
-            uint32_t max_len = 0;
-            {
-                std::lock_guard<std::mutex> lk(nd.mu);
-                for (size_t i = 0; i < n; i++) {
-                    if (!nd.store_get(hashes[c0 + i], snap[i])) continue;
-                    ok[i] = 1;
-                    max_len = std::max<uint32_t>(max_len, (uint32_t)snap[i].bytes.size());
-                }
-            }
-            const size_t stride = garage_ec_stride_for(max_len);
             uint8_t *buf = scrub_buf.get(n * stride + n * 32 + n + n * 4);
             if (!buf) return GARAGE_EC_E_NOMEM;
             uint8_t *expect = buf + n * stride, *bad = expect + n * 32;
             std::vector<uint32_t> lens(n, 0);
-            for (size_t i = 0; i < n; i++) {
-                if (!ok[i]) {
+            std::vector<uint8_t> state(n, 0);  // 0 gone, 1 to be checked on the GPU, 2 corrupt already, 3 checked on the CPU
+            {
+                std::lock_guard<std::mutex> lk(nd.mu);
+                for (size_t i = 0; i < n; i++) {
+                    ShardMeta mt;
                     memset(expect + i * 32, 0, 32);
-                    continue;
+                    const ReadResult r = nd.store_read_into(hashes[c0 + i], buf + i * stride, stride, mt);
+                    if (r == kReadMissing) continue;
+                    if (r == kReadInvalid) {
+                        state[i] = 2;
+                        continue;
+                    }
+                    lens[i] = mt.shard_len;
+                    bytes_read += mt.shard_len;
+                    if (mt.sum_kind == sum_kind) {
+                        memcpy(expect + i * 32, mt.sum.data(), 32);
+                        state[i] = 1;
+                    } else {  // written under another tag kind: check it on the CPU
+                        Hash got;
+                        garage_ec_shard_sum_host(mt.sum_kind, buf + i * stride, mt.shard_len, got.data());
+                        state[i] = got == mt.sum ? 3 : 2;
+                        lens[i] = 0;
+                    }
                 }
-                lens[i] = (uint32_t)snap[i].bytes.size();
-                memcpy(buf + i * stride, snap[i].bytes.data(), lens[i]);
-                memcpy(expect + i * 32, snap[i].sum.data(), 32);
-                bytes_read += lens[i];
             }
             int rc = garage_ec_check_sums(ec, buf, expect, lens.data(), stride, n, 1, bad, GARAGE_EC_MEM_HOST, nullptr);
             if (rc != GARAGE_EC_OK) return rc;
             for (size_t i = 0; i < n; i++) {
-                if (!ok[i]) continue;
+                if (!state[i]) continue;
                 nchecked++;
-                if (!bad[i]) continue;
+                if (state[i] == 3 || (state[i] == 1 && !bad[i])) continue;
                 nbad++;
-                corruption_counter++;
-                {
-                    std::lock_guard<std::mutex> lk(nd.mu);
-                    nd.store_quarantine(hashes[c0 + i]);
-                }
-                put_to_resync(node, hashes[c0 + i]);
+                quarantine(node, hashes[c0 + i]);
             }
         }
         scrub_checked += nchecked;
@@ -899,9 +1148,92 @@ struct garage_bm {
         if (corrupt) *corrupt = nbad;
         return GARAGE_BM_OK;
     }
+
+    // ---- native closed-loop load generator (tools/bm_bench.py drives it): `threads` client threads,
+    // each PUTs (mode 0) or GETs (mode 1) `per_thread` blocks of `block_len` bytes.  Blocks are the
+    // splitmix64 stream (seed, thread, i); hashing them is the S3 layer's job (put.rs:448) and
+    // happens before the clock starts.
+    int bench(int threads, int per_thread, uint32_t block_len, int mode, uint64_t seed, double *gib_per_s, uint64_t *errors)
+    {
+        if (threads < 1 || per_thread < 1 || block_len < 1 || shard_len_of(block_len) > slot_stride) return GARAGE_EC_E_INVALID;
+        const size_t nb = (size_t)threads * per_thread;
+        std::vector<uint8_t> data;
+        std::vector<Hash> hashes(nb);
+        const size_t words = ((size_t)block_len + 7) / 8;
+        if (mode == 0) data.resize(nb * words * 8);
+        auto gen = [&](size_t b, uint8_t *dst) {
+            uint64_t *w = reinterpret_cast<uint64_t *>(dst);
+            for (size_t i = 0; i < words; i++) {
+                uint64_t z = seed + (b * words + i + 1) * 0x9E3779B97F4A7C15ull;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                w[i] = z ^ (z >> 31);
+            }
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; t++)
+                th.emplace_back([&, t] {
+                    std::vector<uint8_t> tmp(words * 8);
+                    for (int i = 0; i < per_thread; i++) {
+                        const size_t b = (size_t)t * per_thread + i;
+                        uint8_t *dst = mode == 0 ? data.data() + b * words * 8 : tmp.data();
+                        gen(b, dst);
+                        garage_ec_blake2sum(dst, block_len, hashes[b].data());
+                    }
+                });
+            for (auto &x : th) x.join();
+        }
+        std::atomic<uint64_t> errs{0};
+        std::atomic<int> ready{0};
+        std::atomic<bool> go{false};
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++)
+            th.emplace_back([&, t] {
+                garage_ec_bind_thread(ec);
+                std::vector<uint8_t> out(mode == 1 ? block_len : 0);
+                ready++;
+                while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+                for (int i = 0; i < per_thread; i++) {
+                    const size_t b = (size_t)t * per_thread + i;
+                    int rc;
+                    try {
+                        if (mode == 0) {
+                            rc = rpc_put_block(hashes[b], data.data() + b * words * 8, block_len);
+                        } else {
+                            size_t n = 0;
+                            rc = rpc_get_block(hashes[b], out.data(), out.size(), &n);
+                            if (rc == GARAGE_BM_OK && n != block_len) rc = GARAGE_BM_E_CORRUPT_DATA;
+                        }
+                    } catch (...) {
+                        rc = GARAGE_EC_E_NOMEM;
+                    }
+                    if (rc != GARAGE_BM_OK) errs++;
+                }
+            });
+        while (ready.load() < threads) std::this_thread::yield();
+        const auto t0 = Clock::now();
+        go.store(true, std::memory_order_release);
+        for (auto &x : th) x.join();
+        const double el = std::chrono::duration<double>(Clock::now() - t0).count();
+        if (gib_per_s) *gib_per_s = (double)nb * block_len / el / (double)(1ull << 30);
+        if (errors) *errors = errs.load();
+        return GARAGE_BM_OK;
+    }
 };
 
 // ================================================================= C API
+// Nothing throws across the C boundary (the reference returns Result everywhere,
+// src/util/error.rs:14-82): allocation failures and anything unexpected become status codes.
+#define BM_GUARD(expr)                       \
+    try {                                    \
+        return (expr);                       \
+    } catch (const std::bad_alloc &) {       \
+        return GARAGE_EC_E_NOMEM;            \
+    } catch (...) {                          \
+        return GARAGE_BM_E_MESSAGE;          \
+    }
+
 extern "C" {
 
 void garage_bm_default_config(garage_bm_config *c)
@@ -916,26 +1248,36 @@ void garage_bm_default_config(garage_bm_config *c)
     c->batch_max_blocks = 64;
     c->batch_linger_us = 200;
     c->data_dir = nullptr;
+    c->shard_sum_kind = GARAGE_EC_SUM_ADLER8;
+    c->verify_content_hash = 1;
+    c->data_fsync = 0;             // util/config.rs data_fsync default
+    c->block_gc_delay_ms = 600000;  // BLOCK_GC_DELAY, manager.rs:49-52
 }
 
-int garage_bm_create(garage_bm **out, const garage_bm_config *cfg)
+static int bm_create(garage_bm **out, const garage_bm_config *cfg)
 {
-    if (!out || !cfg) return GARAGE_EC_E_INVALID;
     *out = nullptr;
     const int k = cfg->data_shards, m = cfg->parity_shards;
-    if (k < 1 || m < 1 || k + m > 40 || cfg->n_nodes < k + m || cfg->n_nodes > 256) return GARAGE_EC_E_INVALID;
+    if (k < 1 || m < 1 || k > GARAGE_EC_MAX_K || m > GARAGE_EC_MAX_M || cfg->n_nodes < k + m || cfg->n_nodes > 256)
+        return GARAGE_EC_E_INVALID;
+    if (cfg->shard_sum_kind != GARAGE_EC_SUM_BLAKE2 && cfg->shard_sum_kind != GARAGE_EC_SUM_ADLER8) return GARAGE_EC_E_INVALID;
     std::unique_ptr<garage_bm> bm(new garage_bm());
     bm->cfg = *cfg;
+    if (!bm->cfg.block_size) bm->cfg.block_size = 1u << 20;
     bm->k = k;
     bm->m = m;
     bm->tot = k + m;
+    bm->sum_kind = cfg->shard_sum_kind;
+    bm->slot_stride = garage_ec_stride_for(garage_ec_shard_len(bm->cfg.block_size, k));
     int rc = garage_ec_create(&bm->ec, cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
     if (rc != GARAGE_EC_OK) return rc;  // no GPU => no block manager: there is no CPU fallback
+    garage_ec_set_sum_kind(bm->ec, bm->sum_kind);
     for (int i = 0; i < cfg->n_nodes; i++) {
         bm->nodes.emplace_back(new Node());
         Node &nd = *bm->nodes.back();
         nd.k = k;
         nd.m = m;
+        nd.fsync_data = cfg->data_fsync != 0;
         if (cfg->data_dir && cfg->data_dir[0]) {
             nd.dir = std::string(cfg->data_dir) + "/node" + std::to_string(i);
             std::error_code ec;
@@ -943,36 +1285,44 @@ int garage_bm_create(garage_bm **out, const garage_bm_config *cfg)
             // restart: what is on disk is what exists (the block_ref table would say the same)
             std::vector<Hash> have;
             nd.store_list(have);
+            std::vector<uint8_t> tmp(bm->slot_stride);
             for (const Hash &h : have) {
-                StoredShard sh;
-                if (nd.store_get(h, sh)) bm->refs[h] = sh.block_len;
+                ShardMeta mt;
+                if (nd.store_read_into(h, tmp.data(), tmp.size(), mt) == kReadOk) bm->refs[h] = mt.block_len;
             }
         }
     }
     bm->ram.reset(new ByteSemaphore(cfg->block_ram_buffer_max ? cfg->block_ram_buffer_max : (256ull << 20)));
     bm->scrub_buf.ctx = bm->ec;
+    auto destroy_on_error = [&](int code) {
+        garage_bm_destroy(bm.release());
+        return code;
+    };
     for (int w = 0; w < garage_bm::kWorkers; w++) {
         rc = garage_ec_create(&bm->enc_ctx[w], cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
         if (rc == GARAGE_EC_OK) rc = garage_ec_create(&bm->rec_ctx[w], cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
-        if (rc != GARAGE_EC_OK) {
-            garage_bm_destroy(bm.release());
-            return rc;
-        }
-        bm->enc_parity[w].ctx = bm->enc_ctx[w];
-        bm->rec_buf[w].ctx = bm->rec_ctx[w];
+        if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
+        garage_ec_set_sum_kind(bm->enc_ctx[w], bm->sum_kind);
+        garage_ec_set_sum_kind(bm->rec_ctx[w], bm->sum_kind);
+        bm->enc_out[w][0].ctx = bm->enc_out[w][1].ctx = bm->enc_ctx[w];
     }
     const size_t nslots = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * (garage_bm::kWorkers + 1);
-    if (!bm->slots.init(bm->ec, nslots, cfg->block_size ? cfg->block_size : (1u << 20))) {
-        garage_bm_destroy(bm.release());
-        return GARAGE_EC_E_NOMEM;
-    }
+    if (!bm->put_slots.init(bm->ec, nslots, bm->cfg.block_size)) return destroy_on_error(GARAGE_EC_E_NOMEM);
+    if (!bm->stripe_slots.init(bm->ec, nslots, (size_t)bm->tot * bm->slot_stride)) return destroy_on_error(GARAGE_EC_E_NOMEM);
     garage_bm *raw = bm.get();
+    auto bind = [raw] { garage_ec_bind_thread(raw->ec); };
     bm->enc_batcher.reset(new Batcher<EncodeItem>(cfg->batch_max_blocks, cfg->batch_linger_us, garage_bm::kWorkers,
-                                                  [raw](int w, std::vector<EncodeItem *> &b) { raw->run_encode(w, b); }));
+                                                  [raw](int w, std::vector<EncodeItem *> &b) { raw->run_encode(w, b); }, bind));
     bm->rec_batcher.reset(new Batcher<ReconItem>(cfg->batch_max_blocks, cfg->batch_linger_us, garage_bm::kWorkers,
-                                                 [raw](int w, std::vector<ReconItem *> &b) { raw->run_reconstruct(w, b); }));
+                                                 [raw](int w, std::vector<ReconItem *> &b) { raw->run_reconstruct(w, b); }, bind));
     *out = bm.release();
     return GARAGE_BM_OK;
+}
+
+int garage_bm_create(garage_bm **out, const garage_bm_config *cfg)
+{
+    if (!out || !cfg) return GARAGE_EC_E_INVALID;
+    BM_GUARD(bm_create(out, cfg));
 }
 
 void garage_bm_destroy(garage_bm *bm)
@@ -983,17 +1333,18 @@ void garage_bm_destroy(garage_bm *bm)
     garage_ec_ctx *ec = bm->ec;
     garage_ec_ctx *ctxs[2 * garage_bm::kWorkers];
     for (int w = 0; w < garage_bm::kWorkers; w++) {
-        bm->enc_parity[w].release();  // pinned buffers go before their context
-        bm->rec_buf[w].release();
+        bm->enc_out[w][0].release();  // pinned buffers go before their context
+        bm->enc_out[w][1].release();
         ctxs[2 * w] = bm->enc_ctx[w];
         ctxs[2 * w + 1] = bm->rec_ctx[w];
     }
     bm->scrub_buf.release();
-    bm->slots.destroy();
+    bm->put_slots.destroy();
+    bm->stripe_slots.destroy();
     delete bm;
     for (garage_ec_ctx *c : ctxs)
         if (c) garage_ec_destroy(c);
-    garage_ec_destroy(ec);
+    if (ec) garage_ec_destroy(ec);
 }
 
 void garage_bm_blake2sum(const uint8_t *data, size_t len, uint8_t hash_out[32]) { garage_ec_blake2sum(data, len, hash_out); }
@@ -1001,74 +1352,79 @@ void garage_bm_blake2sum(const uint8_t *data, size_t len, uint8_t hash_out[32]) 
 int garage_bm_rpc_put_block(garage_bm *bm, const uint8_t hash[32], const uint8_t *data, size_t len)
 {
     if (!bm || !hash || !data) return GARAGE_EC_E_INVALID;
-    return bm->rpc_put_block(to_hash(hash), data, len);
+    BM_GUARD(bm->rpc_put_block(to_hash(hash), data, len));
 }
 
 int garage_bm_rpc_get_block(garage_bm *bm, const uint8_t hash[32], uint8_t *out, size_t cap, size_t *out_len)
 {
-    if (!bm || !hash || !out_len) return GARAGE_EC_E_INVALID;
-    std::vector<uint8_t> v;
-    int rc = bm->rpc_get_block(to_hash(hash), v);
-    if (rc != GARAGE_BM_OK) return rc;
-    *out_len = v.size();
-    if (v.size() > cap || !out) return GARAGE_EC_E_INVALID;
-    memcpy(out, v.data(), v.size());
-    return GARAGE_BM_OK;
+    if (!bm || !hash || !out_len || !out) return GARAGE_EC_E_INVALID;
+    BM_GUARD(bm->rpc_get_block(to_hash(hash), out, cap, out_len));
 }
 
 int garage_bm_resync_block(garage_bm *bm, int node, const uint8_t hash[32])
 {
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
-    return bm->resync_block(node, to_hash(hash));
+    BM_GUARD(bm->resync_block(node, to_hash(hash)));
 }
 
 int garage_bm_block_incref(garage_bm *bm, const uint8_t hash[32])
 {
     if (!bm || !hash) return GARAGE_EC_E_INVALID;
-    bm->block_incref(to_hash(hash));
-    return GARAGE_BM_OK;
+    BM_GUARD((bm->block_incref(to_hash(hash)), GARAGE_BM_OK));
 }
 
 int garage_bm_block_decref(garage_bm *bm, const uint8_t hash[32])
 {
     if (!bm || !hash) return GARAGE_EC_E_INVALID;
-    bm->block_decref(to_hash(hash));
-    return GARAGE_BM_OK;
+    BM_GUARD((bm->block_decref(to_hash(hash)), GARAGE_BM_OK));
 }
 
 long long garage_bm_get_block_rc(garage_bm *bm, const uint8_t hash[32])
 {
     if (!bm || !hash) return -1;
-    return (long long)bm->get_block_rc(to_hash(hash));
+    BM_GUARD((long long)bm->get_block_rc(to_hash(hash)));
 }
 
 int garage_bm_resync_all(garage_bm *bm, int node, int workers, uint64_t *resynced)
 {
     if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
-    return bm->resync_all(node, workers, resynced);
+    BM_GUARD(bm->resync_all(node, workers, resynced));
 }
 
 int garage_bm_repair_enqueue_missing(garage_bm *bm, int node, uint64_t *enqueued)
 {
     if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
-    return bm->repair_enqueue_missing(node, enqueued);
+    BM_GUARD(bm->repair_enqueue_missing(node, enqueued));
 }
 
 int garage_bm_scrub(garage_bm *bm, int node, uint64_t *checked, uint64_t *corrupt)
 {
     if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
-    return bm->scrub(node, checked, corrupt);
+    BM_GUARD(bm->scrub(node, checked, corrupt));
 }
 
 int garage_bm_scrub_step(garage_bm *bm, int node, const uint8_t *cursor32, size_t max_shards, uint8_t cursor_out32[32],
                          int *finished, uint64_t *checked, uint64_t *corrupt)
 {
     if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
-    Hash cur, out;
-    if (cursor32) cur = to_hash(cursor32);
-    int rc = bm->scrub(node, checked, corrupt, cursor32 ? &cur : nullptr, max_shards, &out, finished);
-    if (rc == GARAGE_BM_OK && cursor_out32) memcpy(cursor_out32, out.data(), 32);
-    return rc;
+    try {
+        Hash cur, out;
+        if (cursor32) cur = to_hash(cursor32);
+        int rc = bm->scrub(node, checked, corrupt, cursor32 ? &cur : nullptr, max_shards, &out, finished);
+        if (rc == GARAGE_BM_OK && cursor_out32) memcpy(cursor_out32, out.data(), 32);
+        return rc;
+    } catch (const std::bad_alloc &) {
+        return GARAGE_EC_E_NOMEM;
+    } catch (...) {
+        return GARAGE_BM_E_MESSAGE;
+    }
+}
+
+int garage_bm_bench(garage_bm *bm, int threads, int blocks_per_thread, uint32_t block_len, int mode, uint64_t seed,
+                    double *gib_per_s, uint64_t *errors)
+{
+    if (!bm || (mode != 0 && mode != 1)) return GARAGE_EC_E_INVALID;
+    BM_GUARD(bm->bench(threads, blocks_per_thread, block_len, mode, seed, gib_per_s, errors));
 }
 
 int garage_bm_set_node_up(garage_bm *bm, int node, int up)
@@ -1079,16 +1435,95 @@ int garage_bm_set_node_up(garage_bm *bm, int node, int up)
     return GARAGE_BM_OK;
 }
 
+// fault injection: what = 0 flips a bit of the shard's bytes at byte_off, 1 rewrites the stored
+// block_len (+1), 2 rewrites the stored index (+1 mod k+m); the stored tag / header check are left
+// alone in every case -- that is the corruption.
+static int bm_corrupt(garage_bm *bm, int node, const uint8_t hash[32], size_t byte_off, int what)
+{
+    Node &nd = *bm->nodes[node];
+    std::lock_guard<std::mutex> lk(nd.mu);
+    const Hash h = to_hash(hash);
+    if (nd.dir.empty()) {
+        auto it = nd.shards.find(h);
+        if (it == nd.shards.end()) return GARAGE_BM_E_MISSING_BLOCK;
+        if (what == 0) {
+            if (it->second.bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
+            it->second.bytes[byte_off % it->second.bytes.size()] ^= 0x01;
+        } else if (what == 1) {
+            it->second.block_len += 1;
+        } else {
+            it->second.index = (it->second.index + 1) % (bm->tot);
+        }
+        return GARAGE_BM_OK;
+    }
+    FILE *f = fopen(nd.path_of(h, ".shard").c_str(), "r+b");
+    if (!f) return GARAGE_BM_E_MISSING_BLOCK;
+    ShardFileHeader hd;
+    int rc = GARAGE_BM_E_MISSING_BLOCK;
+    if (fread(&hd, sizeof(hd), 1, f) == 1) {
+        long off = -1;
+        uint8_t b = 0;
+        if (what == 0 && hd.shard_len) off = (long)sizeof(hd) + (long)(byte_off % hd.shard_len);
+        else if (what == 1) off = offsetof(ShardFileHeader, block_len);
+        else if (what == 2) off = offsetof(ShardFileHeader, index);
+        if (off >= 0 && fseek(f, off, SEEK_SET) == 0 && fread(&b, 1, 1, f) == 1) {
+            b = what == 0 ? (uint8_t)(b ^ 1) : (uint8_t)(b + 1);
+            if (fseek(f, off, SEEK_SET) == 0 && fwrite(&b, 1, 1, f) == 1) rc = GARAGE_BM_OK;
+        }
+    }
+    fclose(f);
+    return rc;
+}
+
 int garage_bm_corrupt_shard(garage_bm *bm, int node, const uint8_t hash[32], size_t byte_off)
 {
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
+    BM_GUARD(bm_corrupt(bm, node, hash, byte_off, 0));
+}
+
+int garage_bm_corrupt_shard_header(garage_bm *bm, int node, const uint8_t hash[32], int what)
+{
+    if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size() || (what != 1 && what != 2)) return GARAGE_EC_E_INVALID;
+    BM_GUARD(bm_corrupt(bm, node, hash, 0, what));
+}
+
+// replace the shard stored on `node` with a VALID shard (correct tag, correct index) of other
+// content -- the "stale shard / wrong shard written by an earlier bad resync" case that only the
+// whole-block content hash can catch
+int garage_bm_plant_stale_shard(garage_bm *bm, int node, const uint8_t hash[32])
+{
+    if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
+    try {
+        Node &nd = *bm->nodes[node];
+        std::lock_guard<std::mutex> lk(nd.mu);
+        StoredShard sh;
+        const Hash h = to_hash(hash);
+        if (!nd.store_get(h, sh) || sh.bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
+        for (size_t i = 0; i < sh.bytes.size(); i += 97) sh.bytes[i] ^= 0x5a;
+        garage_ec_shard_sum_host(sh.sum_kind, sh.bytes.data(), sh.bytes.size(), sh.sum.data());
+        return nd.store_put(h, sh, sh.bytes.data(), sh.bytes.size()) ? GARAGE_BM_OK : GARAGE_BM_E_MESSAGE;
+    } catch (...) {
+        return GARAGE_EC_E_NOMEM;
+    }
+}
+
+int garage_bm_set_node_readonly(garage_bm *bm, int node, int readonly)
+{
+    if (!bm || node < 0 || node >= (int)bm->nodes.size()) return GARAGE_EC_E_INVALID;
     Node &nd = *bm->nodes[node];
     std::lock_guard<std::mutex> lk(nd.mu);
-    StoredShard sh;
-    if (!nd.store_get(to_hash(hash), sh) || sh.bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
-    sh.bytes[byte_off % sh.bytes.size()] ^= 0x01;  // the stored sum is left alone: that is the corruption
-    nd.store_put(to_hash(hash), std::move(sh));
-    return GARAGE_BM_OK;
+    if (nd.dir.empty()) return GARAGE_BM_E_MESSAGE;  // only meaningful for the file store
+    // works for root too (which ignores permission bits): the directory is moved aside and a plain
+    // FILE takes its name, so every create / open below it fails with ENOTDIR
+    const std::string saved = nd.dir + ".moved_aside";
+    if (readonly) {
+        if (::rename(nd.dir.c_str(), saved.c_str()) != 0) return GARAGE_BM_E_MESSAGE;
+        FILE *f = fopen(nd.dir.c_str(), "wb");
+        if (f) fclose(f);
+        return f ? GARAGE_BM_OK : GARAGE_BM_E_MESSAGE;
+    }
+    ::remove(nd.dir.c_str());
+    return ::rename(saved.c_str(), nd.dir.c_str()) == 0 ? GARAGE_BM_OK : GARAGE_BM_E_MESSAGE;
 }
 
 int garage_bm_drop_shard(garage_bm *bm, int node, const uint8_t hash[32])
@@ -1106,10 +1541,14 @@ int garage_bm_drop_shard(garage_bm *bm, int node, const uint8_t hash[32])
 int garage_bm_node_shard_index(garage_bm *bm, int node, const uint8_t hash[32])
 {
     if (!bm || !hash || node < 0 || node >= (int)bm->nodes.size()) return -1;
-    Node &nd = *bm->nodes[node];
-    std::lock_guard<std::mutex> lk(nd.mu);
-    StoredShard sh;
-    return nd.store_get(to_hash(hash), sh) ? sh.index : -1;
+    try {
+        Node &nd = *bm->nodes[node];
+        std::lock_guard<std::mutex> lk(nd.mu);
+        StoredShard sh;
+        return nd.store_get(to_hash(hash), sh) ? sh.index : -1;
+    } catch (...) {
+        return -1;
+    }
 }
 
 int garage_bm_storage_nodes_of(garage_bm *bm, const uint8_t hash[32], int *nodes_out)
@@ -1138,6 +1577,8 @@ void garage_bm_get_metrics(garage_bm *bm, garage_bm_metrics *o)
     o->scrub_corruptions = bm->scrub_corrupt;
     o->encode_call_us = bm->enc_gpu_us;
     o->reconstruct_call_us = bm->rec_gpu_us;
+    o->corrupt_data_errors = bm->corrupt_data_errors;
+    o->write_errors = bm->write_errors;
     uint64_t ql = 0;
     for (auto &n : bm->nodes) {
         std::lock_guard<std::mutex> lk(n->mu);

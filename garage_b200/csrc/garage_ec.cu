@@ -802,10 +802,16 @@ int garage_ec_verify(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mismat
 }
 
 // --------------------------------------------------------------------------- RECONSTRUCT
-static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *present,
+// `stripes` != NULL: stripe s lives at stripes[s] (its k+m shards `stride` apart) instead of
+// shards + s*(k+m)*stride -- the gather form used by batching front-ends whose callers each own
+// a pinned slot (garage_ec_reconstruct_stripes)
+static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, uint8_t *const *stripes, const uint8_t *present,
                             const uint8_t *want, int32_t *status, const uint32_t *shard_len,
                             size_t stride, size_t n)
 {
+    auto shard_at = [&](size_t s, size_t i) -> uint8_t * {
+        return stripes ? stripes[s] + i * stride : shards + (s * (size_t)(ctx->k + ctx->m) + i) * stride;
+    };
     // declared before the lane lease: they must outlive the stream work the lease waits for
     std::vector<int32_t> st_host(status ? 0 : n);
     CopyBatch up, down;
@@ -842,7 +848,7 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
             size_t used = 0;
             for (size_t i = 0; i < tot && used < k; i++) {
                 if (!pr[i]) continue;
-                up.add(d_sh + ((s - s0) * tot + i) * stride, shards + (s * tot + i) * stride, stride);
+                up.add(d_sh + ((s - s0) * tot + i) * stride, shard_at(s, i), stride);
                 used++;
             }
         }
@@ -880,7 +886,7 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *
             const size_t bytes = align_up(len, 16);
             for (size_t i = 0; i < tot; i++) {
                 if (pr[i] || (want && !want[s * tot + i])) continue;
-                down.add(shards + (s * tot + i) * stride, d_sh + ((s - s0) * tot + i) * stride, bytes);
+                down.add(shard_at(s, i), d_sh + ((s - s0) * tot + i) * stride, bytes);
             }
         }
         rc = down.flush(ctx, cudaMemcpyDeviceToHost, L.stream);
@@ -905,7 +911,7 @@ int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *pr
     if (!aligned16(shards)) return GARAGE_EC_E_ALIGN;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (mem_kind == GARAGE_EC_MEM_HOST)
-        return reconstruct_host(ctx, shards, present, want, status, shard_len, stride, n_stripes);
+        return reconstruct_host(ctx, shards, nullptr, present, want, status, shard_len, stride, n_stripes);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     void *scratch = nullptr;
     CU_TRY(ctx, cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
@@ -917,6 +923,23 @@ int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *pr
     if (rc) return rc;
     if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFreeAsync");
     return GARAGE_EC_OK;
+}
+
+int garage_ec_reconstruct_stripes(garage_ec_ctx *ctx, uint8_t *const *stripes, const uint8_t *present,
+                                  const uint8_t *want, int32_t *status, const uint32_t *shard_len, size_t stride,
+                                  size_t n_stripes)
+{
+    if (!ctx) return GARAGE_EC_E_INVALID;
+    int rc = check_geometry(ctx, stride, n_stripes, ctx->k + ctx->m);
+    if (rc) return rc;
+    if (n_stripes == 0) return GARAGE_EC_OK;
+    if (!stripes || !present) return GARAGE_EC_E_INVALID;
+    for (size_t s = 0; s < n_stripes; s++) {
+        if (!stripes[s]) return GARAGE_EC_E_INVALID;
+        if (!aligned16(stripes[s])) return GARAGE_EC_E_ALIGN;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return reconstruct_host(ctx, nullptr, stripes, present, want, status, shard_len, stride, n_stripes);
 }
 
 // --------------------------------------------------------------------------- SHARD SUMS

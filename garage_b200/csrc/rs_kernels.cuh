@@ -76,7 +76,7 @@ namespace garage_ec {
 #define GEC_LDG_MAXLG 3  // LDG path: largest table group = 2^3 tables (64 contiguous bytes per shard and instruction)
 #endif
 #ifndef GEC_TMA_FROM_K
-#define GEC_TMA_FROM_K 13  // encode / reconstruct use the TMA staging from this k on
+#define GEC_TMA_FROM_K 5  // encode / reconstruct use the TMA staging from this k on (sweep r02_s2: k <= 4 is as fast with LDG)
 #endif
 
 constexpr int kMaxK = 32;
@@ -146,12 +146,26 @@ struct PlanSlot {
 };
 constexpr uint32_t kAuxBytes = 2 * sizeof(PlanSlot) + 8 * (4 + 32) + 64;  // plan slots + mbarriers
 
-// consumer warps.  LDG shapes from the round-1 sweeps (2 x S x 4 registers of column data per thread);
-// TMA: S x 4 registers of column data, capped by the stage memory.
+// Which way the columns reach the lanes, and how many warps stream, per (k, mode): picked from
+// the sweeps on B200 (profiles/r02_sweep_tma_ldg_warps.log: both paths x 8..32 warps for
+// k = 4, 6, 8, 10, 12).
+__host__ __device__ constexpr bool cfg_default_tma(int k, int mode)
+{
+    if (mode == kModeVerify) return k > 6;  // verify: LDG with prefetch wins up to k = 6
+    return k >= GEC_TMA_FROM_K;
+}
 __host__ __device__ constexpr int cfg_nw_ldg(int k, int mode)
 {
-    if (mode == kModeVerify) return k <= 11 ? 32 : 16;
+    if (mode == kModeVerify) return k <= 4 ? 24 : 16;
     return k <= 4 ? 32 : (k <= 6 ? 24 : (k <= 8 ? 20 : 16));
+}
+// TMA path, k <= 12: measured optimum (total warps; reconstruct includes the builder warp and is then
+// clamped to what the stage memory allows); larger k: by register budget (cfg_nw_tma)
+__host__ __device__ constexpr int cfg_nw_tma_small(int k, int mode)
+{
+    if (mode == kModePlan) return k <= 6 ? 32 : (k <= 8 ? 28 : 24);
+    if (mode == kModeVerify) return k <= 8 ? 20 : 16;
+    return k <= 8 ? 20 : 16;
 }
 // TMA: at most 3 table groups per buffer, fewer (= more zero-table padding) when the table buffers
 // would not leave room for the stages of at least 8 consumer warps
@@ -188,7 +202,7 @@ __host__ __device__ constexpr int cfg_fit_nw(int nw, uint32_t tab_bytes, int sta
 // ---- launch shape / shared-memory carve-up per (K, MODE), all compile time ------------------
 template <int K, int MODE> struct StreamCfg {
     static constexpr int kTmaOverride = MODE == kModeEncode ? GEC_TMA_ENC : (MODE == kModePlan ? GEC_TMA_PLAN : GEC_TMA_VER);
-    static constexpr bool kTma = K > 16 || (kTmaOverride >= 0 ? (kTmaOverride != 0) : (MODE == kModeVerify || K >= GEC_TMA_FROM_K));
+    static constexpr bool kTma = K > 16 || (kTmaOverride >= 0 ? (kTmaOverride != 0) : cfg_default_tma(K, MODE));
     static constexpr int kBufs = MODE == kModePlan ? 2 : 1;  // table buffers
     static constexpr int kStageRows = kTma ? K + (MODE == kModeVerify ? kRowsPerPass : 0) : 0;
     static constexpr int kNwOverride = MODE == kModeEncode ? GEC_NW_ENC : (MODE == kModePlan ? GEC_NW_PLAN : GEC_NW_VER);
@@ -204,7 +218,10 @@ template <int K, int MODE> struct StreamCfg {
 
     // consumer warps: LDG shapes from the round-1 sweeps (2 x S x 4 registers of column data);
     // TMA: S x 4 registers of column data, capped by the stage memory
-    static constexpr int kWarpsDefault = kTma ? cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows) : cfg_nw_ldg(K, MODE);
+    static constexpr int kWarpsDefault =
+        !kTma ? cfg_nw_ldg(K, MODE)
+              : (K <= 12 ? cfg_fit_nw(cfg_nw_tma_small(K, MODE), kTabBytes, kStageRows, MODE == kModePlan)
+                         : cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows));
     // an override (tuning builds) is clamped to what the stage memory allows
     static constexpr int kWarpsAll =
         kNwOverride > 0 ? (kTma ? cfg_fit_nw(kNwOverride, kTabBytes, kStageRows, MODE == kModePlan) : kNwOverride) : kWarpsDefault;
@@ -463,6 +480,34 @@ __device__ __forceinline__ void build_tables(uint32_t *tab, const uint8_t *coef,
 
 // 16 table lookups for one 16-byte vector; acc[4*w + p] ^= T[byte p of word w]
 //   base = shared address of (group, this lane's bank for this phase); row_bytes = 128
+// The streaming kernels sit at ~75-80 % issue and ~70 % alu-pipe utilisation (ncu, round 2), so
+// the per-byte instruction count is what is left to win:
+//  * GEC_DP4A: the table address  base + byte_p * 128  is ONE integer dot product,
+//    dp4a(word, 0x80 << 8p, base) = base + 128 * byte_p, instead of PRMT (byte extract, alu pipe)
+//    + IMAD (scale and add, fma pipe);
+//  * GEC_XOR3: two sources are accumulated by one three-input LOP3 (a ^ b ^ c).
+#ifndef GEC_DP4A
+#define GEC_DP4A 1
+#endif
+#ifndef GEC_XOR3
+#define GEC_XOR3 1
+#endif
+__device__ __forceinline__ uint32_t table_addr(uint32_t w, int p, uint32_t base, uint32_t row_bytes)
+{
+#if GEC_DP4A
+    (void)row_bytes;
+    return __dp4a(w, 0x80u << (8 * p), base);
+#else
+    const uint32_t x = __byte_perm(w, 0, 0x4440 + p);  // byte p, zero extended (alu pipe)
+    return x * row_bytes + base;                        // IMAD (fma pipe)
+#endif
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 template <bool kFirst>
 __device__ __forceinline__ void lookup16(uint32_t (&acc)[16], const uint4 &d, uint32_t base,
                                          uint32_t row_bytes)
@@ -472,10 +517,26 @@ __device__ __forceinline__ void lookup16(uint32_t (&acc)[16], const uint4 &d, ui
     for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            const uint32_t x = __byte_perm(w[i], 0, 0x4440 + p);  // byte p, zero extended (alu pipe)
-            const uint32_t v = lds_u32(x * row_bytes + base);     // IMAD (fma pipe)
+            const uint32_t v = lds_u32(table_addr(w[i], p, base, row_bytes));
             if (kFirst) acc[4 * i + p] = v;
             else acc[4 * i + p] ^= v;
+        }
+    }
+}
+// two sources at once: acc = acc ^ T_a[..] ^ T_b[..] in one LOP3
+template <bool kFirst>
+__device__ __forceinline__ void lookup16x2(uint32_t (&acc)[16], const uint4 &da, uint32_t base_a, const uint4 &db,
+                                           uint32_t base_b, uint32_t row_bytes)
+{
+    const uint32_t wa[4] = {da.x, da.y, da.z, da.w}, wb[4] = {db.x, db.y, db.z, db.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const uint32_t va = lds_u32(table_addr(wa[i], p, base_a, row_bytes));
+            const uint32_t vb = lds_u32(table_addr(wb[i], p, base_b, row_bytes));
+            if (kFirst) acc[4 * i + p] = va ^ vb;
+            else acc[4 * i + p] = xor3(acc[4 * i + p], va, vb);
         }
     }
 }
@@ -547,15 +608,28 @@ __device__ __forceinline__ void column_compute(uint4 (&d)[CFG::S], uint32_t tab_
 #pragma unroll
         for (int u = 0; u < CFG::S; u++) d[u] = mask_tail(d[u], tail_bytes);
     }
-    static_for<0, CFG::S>([&](auto uc) {
+    // this lane's bank at phase ph of group g: lane xor ph*R
+    auto slot_base = [&](auto uc) -> uint32_t {
         constexpr int u = decltype(uc)::value;
         constexpr int g = slot_group(LAY, u);
         constexpr int lg = LAY.lg[g];
         constexpr int ph = u - LAY.base[g];
-        // this lane's bank at phase ph of group g: lane xor ph*R
-        const uint32_t base = tab_addr + (uint32_t)g * kGroupBytes + ((lane ^ ((uint32_t)ph << (lg ? 5 - lg : 0))) << 2);
-        lookup16<u == 0>(acc, d[u], base, row_bytes);
+        return tab_addr + (uint32_t)g * kGroupBytes + ((lane ^ ((uint32_t)ph << (lg ? 5 - lg : 0))) << 2);
+    };
+#if GEC_XOR3
+    static_for<0, CFG::S / 2>([&](auto pc) {
+        constexpr int u = 2 * decltype(pc)::value;
+        lookup16x2<u == 0>(acc, d[u], slot_base(std::integral_constant<int, u>{}), d[u + 1],
+                           slot_base(std::integral_constant<int, u + 1>{}), row_bytes);
     });
+    if constexpr (CFG::S % 2 == 1)
+        lookup16<CFG::S == 1>(acc, d[CFG::S - 1], slot_base(std::integral_constant<int, CFG::S - 1>{}), row_bytes);
+#else
+    static_for<0, CFG::S>([&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        lookup16<u == 0>(acc, d[u], slot_base(uc), row_bytes);
+    });
+#endif
     rows_from_acc(acc, r);
 }
 

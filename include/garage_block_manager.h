@@ -52,8 +52,14 @@ typedef struct {
     uint32_t batch_max_blocks;      /* f1: max blocks per GPU batch                   */
     uint32_t batch_linger_us;       /* f1: how long the first block of a batch waits  */
     const char *data_dir;           /* NULL/"": shards in memory; else <data_dir>/node<N>/<hh>/<hh>/<hash>.shard
-                                       (64-byte header {GEC1,k,m,index,block_len,shard_len,blake2sum} + bytes;
-                                       tmp-file -> rename, *.corrupted quarantine: manager.rs:720-819)  */
+                                       (64-byte header {GEC1,k,m,index,sum_kind,block_len,shard_len,tag,header check}
+                                       + bytes; tmp-file -> rename, *.corrupted quarantine: manager.rs:720-819)  */
+    int shard_sum_kind;             /* GARAGE_EC_SUM_ADLER8 (default) or GARAGE_EC_SUM_BLAKE2: the per-shard tag  */
+    int verify_content_hash;        /* 1 (default): rpc_get_block checks blake2sum(block) == hash like
+                                       DataBlock::verify (block.rs:69-83) and hunts the bad shard on mismatch     */
+    int data_fsync;                 /* util/config.rs data_fsync: fsync file + directory before/after the rename  */
+    uint32_t block_gc_delay_ms;     /* BLOCK_GC_DELAY (manager.rs:49-52, 10 min): a shard whose block dropped to
+                                       rc 0 is deleted by resync only after this delay                            */
 } garage_bm_config;
 
 typedef struct {
@@ -66,6 +72,8 @@ typedef struct {
     uint64_t scrub_shards_checked, scrub_corruptions;
     uint64_t resync_queue_length;            /* block.resync_queue_length (all nodes)            */
     uint64_t encode_call_us, reconstruct_call_us; /* wall time spent inside garage_ec_* batch calls */
+    uint64_t corrupt_data_errors;            /* GETs whose reassembled block failed the content hash */
+    uint64_t write_errors;                   /* shard writes that failed (ENOSPC, EACCES, ...)      */
 } garage_bm_metrics;
 
 void garage_bm_default_config(garage_bm_config *cfg);
@@ -113,9 +121,23 @@ int garage_bm_scrub(garage_bm *bm, int node, uint64_t *checked, uint64_t *corrup
 int garage_bm_scrub_step(garage_bm *bm, int node, const uint8_t *cursor32, size_t max_shards,
                          uint8_t cursor_out32[32], int *finished, uint64_t *checked, uint64_t *corrupt);
 
+/* native closed-loop load generator (row f1: the batching front-end decides real-world throughput):
+ * `threads` client threads each PUT (mode 0) or GET (mode 1) `blocks_per_thread` blocks of `block_len`
+ * bytes (splitmix64 stream of `seed`; a GET run must follow a PUT run with the same arguments).  The
+ * content hashes are computed before the clock starts (put.rs:448 does that in the API layer).        */
+int garage_bm_bench(garage_bm *bm, int threads, int blocks_per_thread, uint32_t block_len, int mode,
+                    uint64_t seed, double *gib_per_s, uint64_t *errors);
+
 /* fault injection / inspection for tests */
 int garage_bm_set_node_up(garage_bm *bm, int node, int up);
 int garage_bm_corrupt_shard(garage_bm *bm, int node, const uint8_t hash[32], size_t byte_off);
+/* what = 1: stored block_len + 1; what = 2: stored shard index + 1 (header check left alone)          */
+int garage_bm_corrupt_shard_header(garage_bm *bm, int node, const uint8_t hash[32], int what);
+/* overwrite the shard with a self-consistent shard of OTHER content (valid tag, right index): only the
+ * whole-block content hash can notice                                                                 */
+int garage_bm_plant_stale_shard(garage_bm *bm, int node, const uint8_t hash[32]);
+/* file store only: make every write to the node's directory fail (like ENOSPC / EACCES / a lost mount) */
+int garage_bm_set_node_readonly(garage_bm *bm, int node, int readonly);
 int garage_bm_drop_shard(garage_bm *bm, int node, const uint8_t hash[32]);
 int garage_bm_node_shard_index(garage_bm *bm, int node, const uint8_t hash[32]); /* -1 if none */
 int garage_bm_storage_nodes_of(garage_bm *bm, const uint8_t hash[32], int *nodes_out /* k+m */);

@@ -117,6 +117,15 @@ int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *pr
                           const uint8_t *want, int32_t *status, const uint32_t *shard_len,
                           size_t stride, size_t n_stripes, int mem_kind, void *cuda_stream);
 
+/* Gather form of the HOST-mode reconstruct for batching front-ends: every
+ * caller (a GET that lost shards, one of the 8 resync workers, src/block/resync.rs:43) owns its own
+ * buffer -- stripes[s] points at the k+m shards of stripe s, `stride` apart -- and the batch is just the
+ * list of those pointers: nobody copies shards into a contiguous staging array.  Pinned buffers from
+ * garage_ec_host_alloc make the copies DMA-speed.  Same semantics as garage_ec_reconstruct(MEM_HOST). */
+int garage_ec_reconstruct_stripes(garage_ec_ctx *ctx, uint8_t *const *stripes, const uint8_t *present,
+                                  const uint8_t *want, int32_t *status, const uint32_t *shard_len,
+                                  size_t stride, size_t n_stripes);
+
 /* ---- VERIFY (scrub) -- call sites: DataBlock::verify via BlockManager::read_block,
  * src/block/manager.rs:554-609 / src/block/block.rs:69-83, driven by ScrubWorker::work,
  * src/block/repair.rs:438-490: recompute parity from the k data shards and compare with

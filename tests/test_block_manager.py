@@ -225,7 +225,15 @@ def test_file_backed_store_survives_restart(tmp_path):
     assert raw[:4] == b"GEC1" and raw[4] == k and raw[5] == m
     shard_len = int.from_bytes(raw[12:16], "little")
     assert len(raw) == 64 + shard_len
-    assert raw[16:48] == hashlib.blake2b(raw[64:]).digest()[:32]  # per-shard blake2sum in the header
+    # per-shard tag in the header, of the kind byte 7 names (default: adler8 = 8 x zlib Adler-32)
+    import struct
+    import zlib
+
+    assert raw[7] == BM.SUM_ADLER8
+    body = raw[64:]
+    seg = (((len(body) + 7) // 8) + 15) // 16 * 16
+    assert raw[16:48] == b"".join(struct.pack("<I", zlib.adler32(body[i * seg:(i + 1) * seg])) for i in range(8))
+    assert int.from_bytes(raw[48:52], "little") == zlib.adler32(raw[:48])  # header check covers every field
     assert not list((tmp_path / "data").rglob("*.tmp*"))
     with BM.BlockManager(k, m, data_dir=d) as bm:  # "restart"
         for h, b in zip(hashes, blocks):
@@ -298,3 +306,131 @@ def test_scrub_is_resumable_from_a_checkpoint():
         assert bm.metrics()["resync_queue_length"] == 2
         rc, cursor2, finished, checked, corrupt = bm.scrub_step(node, cursor, max_shards=7)
         assert finished and checked == 0 and cursor2 == cursor  # nothing after the last checkpoint
+
+
+@pytest.mark.gpu
+def test_blake2_shard_tags_still_supported(tmp_path):
+    k, m = 4, 2
+    b = O.fill_random(400000, 21)
+    d = str(tmp_path / "data")
+    with BM.BlockManager(k, m, data_dir=d, shard_sum_kind=BM.SUM_BLAKE2) as bm:
+        h = BM.blake2sum(b)
+        assert bm.rpc_put_block(h, b) == BM.OK
+        raw = sorted((tmp_path / "data").rglob("*.shard"))[0].read_bytes()
+        assert raw[7] == BM.SUM_BLAKE2 and raw[16:48] == hashlib.blake2b(raw[64:]).digest()[:32]
+        rc, checked, corrupt = bm.scrub(bm.storage_nodes_of(h)[0])
+        assert (rc, checked, corrupt) == (BM.OK, 1, 0)
+    # a manager configured for adler8 reads (and scrubs, on the CPU) shards written with blake2 tags
+    with BM.BlockManager(k, m, data_dir=d) as bm:
+        rc, got = bm.rpc_get_block(h)
+        assert rc == BM.OK and np.array_equal(got, b)
+        rc, checked, corrupt = bm.scrub(bm.storage_nodes_of(h)[1])
+        assert (rc, checked, corrupt) == (BM.OK, 1, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("in_memory", [True, False])
+def test_get_checks_the_content_hash_and_hunts_the_bad_shard(tmp_path, in_memory):
+    """DataBlock::verify on every read (block.rs:69-83): a shard that passes its OWN tag but holds other
+    bytes (stale / written by a bad resync) must not reach the client.  GET notices through the
+    whole-block blake2sum, finds the culprit by leave-one-out reconstruction, quarantines it, and still
+    returns the right block; resync then rebuilds it."""
+    k, m = 6, 3
+    b = O.fill_random(900001, 33)
+    kw = {} if in_memory else {"data_dir": str(tmp_path / "d")}
+    with BM.BlockManager(k, m, **kw) as bm:
+        h = BM.blake2sum(b)
+        assert bm.rpc_put_block(h, b) == BM.OK
+        who = bm.storage_nodes_of(h)
+        assert bm.plant_stale_shard(who[3], h) == BM.OK  # data shard 3: valid tag, wrong bytes
+        rc, got = bm.rpc_get_block(h)
+        assert rc == BM.OK and np.array_equal(got, b)
+        mt = bm.metrics()
+        assert mt["corrupt_data_errors"] == 1 and mt["corruption_counter"] == 1 and mt["resync_queue_length"] == 1
+        assert bm.node_shard_index(who[3], h) == -1  # quarantined
+        assert bm.resync_all(who[3]) == (0, 1)
+        rc, got = bm.rpc_get_block(h)
+        assert rc == BM.OK and np.array_equal(got, b) and bm.metrics()["corrupt_data_errors"] == 1
+        # more stale shards than the code can route around: CorruptData, never wrong bytes
+        for i in (0, 1, 2, 4):
+            assert bm.plant_stale_shard(who[i], h) == BM.OK
+        rc, got = bm.rpc_get_block(h)
+        assert rc == BM.E_CORRUPT_DATA and got is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("in_memory", [True, False])
+def test_corrupt_shard_metadata_is_caught(tmp_path, in_memory):
+    """flipped block_len / index in a shard's header: covered by the header check (file store) and
+    cross-checked against the other shards, never trusted"""
+    k, m = 4, 2
+    b = O.fill_random(600000, 44)
+    kw = {} if in_memory else {"data_dir": str(tmp_path / "d")}
+    with BM.BlockManager(k, m, **kw) as bm:
+        h = BM.blake2sum(b)
+        assert bm.rpc_put_block(h, b) == BM.OK
+        who = bm.storage_nodes_of(h)
+        assert bm.corrupt_shard_header(who[0], h, 1) == BM.OK  # block_len + 1
+        assert bm.corrupt_shard_header(who[2], h, 2) == BM.OK  # index + 1
+        rc, got = bm.rpc_get_block(h)
+        assert rc == BM.OK and np.array_equal(got, b)
+        assert bm.metrics()["corruption_counter"] == 2 and bm.metrics()["resync_queue_length"] == 2
+        assert bm.resync_all(who[0]) == (0, 1) and bm.resync_all(who[2]) == (0, 1)
+        for n in who:
+            assert bm.scrub(n)[2] == 0
+
+
+@pytest.mark.gpu
+def test_failed_shard_writes_do_not_count_towards_the_quorum(tmp_path):
+    k, m = 4, 2
+    with BM.BlockManager(k, m, data_dir=str(tmp_path / "d"), data_fsync=True) as bm:
+        b = O.fill_random(200000, 5)
+        h = BM.blake2sum(b)
+        who = bm.storage_nodes_of(h)
+        assert bm.rpc_put_block(h, b) == BM.OK and bm.metrics()["write_errors"] == 0
+        b2 = O.fill_random(200000, 6)
+        h2 = BM.blake2sum(b2)
+        who2 = bm.storage_nodes_of(h2)
+        for n in who2[:2]:
+            assert bm.set_node_readonly(n, True) == BM.OK
+        assert bm.rpc_put_block(h2, b2) == BM.E_QUORUM  # 4 stored < k + 1
+        assert bm.metrics()["write_errors"] == 2
+        for n in who2[:2]:
+            bm.set_node_readonly(n, False)
+
+
+@pytest.mark.gpu
+def test_block_gc_delay_protects_a_block_that_is_referenced_again():
+    """BLOCK_GC_DELAY (manager.rs:49-52): a shard whose block dropped to rc 0 is only deleted after the
+    delay, and the decision is re-checked under the locks -- an incref in between keeps the shard."""
+    k, m = 4, 2
+    b = O.fill_random(123456, 8)
+    with BM.BlockManager(k, m, block_gc_delay_ms=60000) as bm:
+        h = BM.blake2sum(b)
+        bm.block_incref(h)
+        assert bm.rpc_put_block(h, b) == BM.OK
+        for node in range(k + m):
+            bm.resync_all(node)
+        bm.block_decref(h)  # rc 0: deletion queued ...
+        for node in range(k + m):
+            assert bm.resync_all(node) == (0, 1)
+            assert bm.node_shard_index(node, h) >= 0  # ... but inside the GC delay nothing is deleted
+        assert bm.metrics()["delete_counter"] == 0 and bm.metrics()["resync_queue_length"] == k + m
+        bm.block_incref(h)  # referenced again (re-upload of the same content)
+        for node in range(k + m):
+            bm.resync_all(node)
+            assert bm.node_shard_index(node, h) >= 0
+        assert bm.metrics()["delete_counter"] == 0
+
+
+@pytest.mark.gpu
+def test_native_load_generator_round_trip():
+    with BM.BlockManager(10, 4, batch_max_blocks=32, batch_linger_us=500) as bm:
+        rc, gibs, errs = bm.bench(8, 6, 1 << 20, 0, seed=3)
+        assert (rc, errs) == (0, 0) and gibs > 0
+        rc, gibs, errs = bm.bench(8, 6, 1 << 20, 1, seed=3)
+        assert (rc, errs) == (0, 0)
+        for d in range(4):
+            bm.set_node_up(d, False)
+        rc, gibs, errs = bm.bench(8, 6, 1 << 20, 1, seed=3)
+        assert (rc, errs) == (0, 0) and bm.metrics()["reconstruct_calls"] > 0
