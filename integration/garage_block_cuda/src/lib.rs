@@ -1,15 +1,16 @@
 //! Safe wrapper with Garage's conventions.  NOT compiled here.
+pub mod batch;   // the batching front-end (row f1): EcBatcher::encode / ::reconstruct are what BlockManager calls
 pub mod sys;
 
 use bytes::Bytes;
 use garage_util::data::Hash;
 use garage_util::error::Error;
 
-pub struct ErasureCoder { ctx: *mut sys::garage_ec_ctx, pub k: usize, pub m: usize }
+pub struct ErasureCoder { pub(crate) ctx: *mut sys::garage_ec_ctx, pub k: usize, pub m: usize }
 unsafe impl Send for ErasureCoder {}   // the C context is internally synchronised
 unsafe impl Sync for ErasureCoder {}
 
-fn check(ctx: *const sys::garage_ec_ctx, rc: i32) -> Result<(), Error> {
+pub(crate) fn check(ctx: *const sys::garage_ec_ctx, rc: i32) -> Result<(), Error> {
     if rc == sys::GARAGE_EC_OK { return Ok(()); }
     let msg = unsafe { std::ffi::CStr::from_ptr(sys::garage_ec_strerror(rc)) }.to_string_lossy();
     let det = unsafe { std::ffi::CStr::from_ptr(sys::garage_ec_last_error(ctx)) }.to_string_lossy();
@@ -45,7 +46,9 @@ impl ErasureCoder {
         }).collect())
     }
 
-    /// GET / resync: `shards[i]` is Some(bytes) for every shard that arrived.  Rebuilds the
+    /// GET / resync, ONE stripe per call: kept for tools and tests.  The block manager goes through
+    /// batch::EcBatcher::reconstruct instead (one FFI call per stripe is the slowest way to drive the GPU).
+    /// `shards[i]` is Some(bytes) for every shard that arrived.  Rebuilds the
     /// shards selected by `want` (data shards for GET, this node's index for resync).
     pub fn reconstruct(&self, hash: &Hash, block_len: usize, shards: &mut [Option<Vec<u8>>], want: &[bool])
         -> Result<(), Error>
