@@ -286,6 +286,46 @@ cudaError_t launch_apply(garage_ec_ctx *ctx, const ApplyParams &p, cudaStream_t 
 
 uint32_t items_per_stripe(size_t stride) { return (uint32_t)((stride / 16 + 31) / 32); }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+using TensorMapEncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder()
+{
+    static std::atomic<void *> cached{nullptr};
+    static std::atomic<int> tried{0};
+    if (!tried.load(std::memory_order_acquire)) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        (void)cudaGetLastError();
+        cached.store(fn, std::memory_order_release);
+        tried.store(1, std::memory_order_release);
+    }
+    return reinterpret_cast<TensorMapEncodeFn>(cached.load(std::memory_order_acquire));
+}
+// 2-D view of a shard array for the TMA path of the uniform kernels: dim0 = stride/4 uint32, dim1 = rows shards.
+// false = no tensor map (the kernel then issues one 1-D bulk copy per row)
+bool make_src_tensor_map(CUtensorMap *tm, const uint8_t *src, size_t stride, size_t rows, int k)
+{
+#if GEC_TMAP
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc || stride < kStageRowBytes || rows == 0 || rows > 0xffffffffull || k > 256) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(stride / 4), (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)stride};
+    const cuuint32_t box[2] = {kStageRowBytes / 4, (cuuint32_t)k};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(src), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#else
+    (void)tm, (void)src, (void)stride, (void)rows, (void)k;
+    return false;
+#endif
+}
+
 // Device-resident encode (mode 0) / verify (mode 2) of n stripes, split so that
 // n * items_per_stripe stays below 2^32 and m > 4 runs in passes of 4 rows.
 int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pitch, uint8_t *dst,
@@ -313,6 +353,8 @@ int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pit
             p.row_off = (uint32_t)r0;
             p.items_per_stripe = ips;
             p.row_bytes = 128;
+            p.rows_per_stripe = (uint32_t)(src_pitch / stride);
+            p.use_tmap = make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe, ctx->k) ? 1u : 0u;
             for (uint32_t i = 0; i < p.rows; i++)
                 memcpy(p.coef + i * ctx->k, ctx->P + (r0 + i) * ctx->k, ctx->k);
             cudaError_t e = mode == kModeEncode ? launch_apply<kModeEncode>(ctx, p, st)
@@ -1185,25 +1227,6 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
 }
 
 // --------------------------------------------------------------------------- BLOCK-LEVEL
-// H2D of one block split into k zero-padded shards at dst (device, shard layout).
-static int upload_block_split(garage_ec_ctx *ctx, const uint8_t *block, uint32_t block_len, size_t k,
-                              uint8_t *dst, size_t stride, uint32_t L, cudaStream_t st)
-{
-    const size_t full = L ? block_len / L : 0;  // shards completely covered by the block
-    const size_t rem = block_len - full * (size_t)L;
-    const size_t Lpad = align_up(L, 16);
-    if (full) {
-        CU_TRY(ctx, cudaMemcpy2DAsync(dst, stride, block, L, L, full < k ? full : k, cudaMemcpyHostToDevice, st));
-    }
-    if (full < k) {
-        uint8_t *d = dst + full * stride;
-        if (rem) CU_TRY(ctx, cudaMemcpyAsync(d, block + full * (size_t)L, rem, cudaMemcpyHostToDevice, st));
-        if (Lpad > rem) CU_TRY(ctx, cudaMemsetAsync(d + rem, 0, Lpad - rem, st));
-        for (size_t j = full + 1; j < k; j++) CU_TRY(ctx, cudaMemsetAsync(dst + j * stride, 0, Lpad, st));
-    }
-    return GARAGE_EC_OK;
-}
-
 int garage_ec_encode_blocks(garage_ec_ctx *ctx, const uint8_t *const *blocks, const uint32_t *block_len,
                             size_t n_blocks, uint8_t *parity_out, size_t stride)
 {
@@ -1219,22 +1242,27 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
     if (n_blocks == 0) return GARAGE_EC_OK;
     if (!blocks || !block_len || !parity_out) return GARAGE_EC_E_INVALID;
     const size_t k = ctx->k, m = ctx->m;
+    uint32_t max_len = 0;
     for (size_t s = 0; s < n_blocks; s++) {
         if (!blocks[s] && block_len[s]) return GARAGE_EC_E_INVALID;
         if (garage_ec_shard_len(block_len[s], (int)k) > stride) return GARAGE_EC_E_INVALID;
+        max_len = block_len[s] > max_len ? block_len[s] : max_len;
     }
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     size_t cs = kHostChunkBytes / (k * stride);
     if (cs < 1) cs = 1;
     if (cs > n_blocks) cs = n_blocks;
-    std::vector<uint32_t> lens(cs * kHostLanes);  // outlives the lane lease below
+    // per lane: [blocks as they arrive, contiguous, `pitch` apart][k data shards][m parity shards]
+    const size_t pitch = align_up((size_t)max_len + 16, 16);  // + one aligned word of slack for the split kernel
+    const size_t blk_b = align_up(cs * pitch, 256), in_b = cs * k * stride, out_b = cs * m * stride;
+    std::vector<uint32_t> lens(2 * cs * kHostLanes);  // [shard_len | block_len] per lane; outlives the lane lease below
+    CopyBatch up;
     LEASE_LANES(ctx, lanes);
-    const size_t in_b = cs * k * stride, out_b = cs * m * stride;
     for (HostLane &L : lanes.set->lanes) {
-        rc = lane_reserve(ctx, L, in_b + out_b, align_up(cs * 4, 16) + cs * (k + m) * 32);
+        rc = lane_reserve(ctx, L, blk_b + in_b + out_b, align_up(cs * 8, 16) + cs * (k + m) * 32);
         if (rc) return rc;
     }
-    const size_t o_sums = align_up(cs * 4, 16);
+    const size_t o_blen = cs * 4, o_sums = align_up(cs * 8, 16);
     size_t c = 0;
     for (size_t s0 = 0; s0 < n_blocks; s0 += cs, c++) {
         const size_t lane_i = c % kHostLanes;
@@ -1242,24 +1270,38 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         const size_t cnt = n_blocks - s0 < cs ? n_blocks - s0 : cs;
         // the pageable `lens` slot of this lane is reused: wait for the lane's previous chunk
         if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
-        uint32_t *hl = lens.data() + lane_i * cs;
+        uint32_t *hl = lens.data() + lane_i * 2 * cs, *hb = hl + cs;
+        uint8_t *d_blk = L.d_buf, *d_data = L.d_buf + blk_b, *d_par = d_data + in_b;
         for (size_t s = 0; s < cnt; s++) {
             hl[s] = garage_ec_shard_len(block_len[s0 + s], (int)k);
-            rc = upload_block_split(ctx, blocks[s0 + s], block_len[s0 + s], k, L.d_buf + s * k * stride,
-                                    stride, hl[s], L.stream);
-            if (rc) return rc;
+            hb[s] = block_len[s0 + s];
+            // H2D: the block as ONE contiguous copy; the framing happens on the device
+            up.add(d_blk + s * pitch, blocks[s0 + s], block_len[s0 + s]);
         }
+        rc = up.flush(ctx, cudaMemcpyHostToDevice, L.stream);
+        if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(L.d_small, hl, cnt * 4, cudaMemcpyHostToDevice, L.stream));
-        rc = run_uniform(ctx, kModeEncode, L.d_buf, k * stride, L.d_buf + in_b, m * stride, nullptr,
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_blen, hb, cnt * 4, cudaMemcpyHostToDevice, L.stream));
+        SplitParams sp;
+        sp.blocks = d_blk;
+        sp.block_len = reinterpret_cast<const uint32_t *>(L.d_small + o_blen);
+        sp.shards = d_data;
+        sp.block_pitch = pitch;
+        sp.stride = (uint32_t)stride;
+        sp.k = (uint32_t)k;
+        sp.n = (uint32_t)cnt;
+        split_blocks_kernel<<<(unsigned)std::min<size_t>(cnt, (size_t)ctx->sm_count * 8), 256, 0, L.stream>>>(sp);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        CU_TRY(ctx, cudaGetLastError());
+        rc = run_uniform(ctx, kModeEncode, d_data, k * stride, d_par, m * stride, nullptr,
                          reinterpret_cast<const uint32_t *>(L.d_small), stride, cnt, L.stream);
         if (rc) return rc;
-        CU_TRY(ctx, cudaMemcpyAsync(parity_out + s0 * m * stride, L.d_buf + in_b, cnt * m * stride,
-                                    cudaMemcpyDeviceToHost, L.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(parity_out + s0 * m * stride, d_par, cnt * m * stride, cudaMemcpyDeviceToHost, L.stream));
         if (sums_out) {
-            // blake2sum of all k+m shards while they are on the device (row f2): [s][k+m][32]
+            // per-shard tags of all k+m shards while they are on the device (row f2): [s][k+m][32]
             const uint32_t *d_len = reinterpret_cast<const uint32_t *>(L.d_small);
-            rc = run_sums(ctx, L.d_buf, nullptr, d_len, stride, cnt * k, (int)k, L.d_small + o_sums, nullptr, L.stream,
-                          (int)(k + m), 0, L.d_buf + in_b, cnt * m, (int)m, (int)k);
+            rc = run_sums(ctx, d_data, nullptr, d_len, stride, cnt * k, (int)k, L.d_small + o_sums, nullptr, L.stream,
+                          (int)(k + m), 0, d_par, cnt * m, (int)m, (int)k);
             if (rc) return rc;
             CU_TRY(ctx, cudaMemcpyAsync(sums_out + s0 * (k + m) * 32, L.d_small + o_sums, cnt * (k + m) * 32,
                                         cudaMemcpyDeviceToHost, L.stream));

@@ -43,6 +43,7 @@
 //    decode-planning kernel; the product tables are built from xtime chains (no log lookups).
 //  * Persistent grid: one CTA per SM.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -71,6 +72,9 @@ namespace garage_ec {
 #endif
 #ifndef GEC_NW_VER
 #define GEC_NW_VER 0
+#endif
+#ifndef GEC_TMAP
+#define GEC_TMAP 1  // uniform modes, TMA path: ONE 2-D tensor copy (k rows x 512 B) per work item instead of k 1-D copies
 #endif
 #ifndef GEC_LDG_MAXLG
 #define GEC_LDG_MAXLG 3  // LDG path: largest table group = 2^3 tables (64 contiguous bytes per shard and instruction)
@@ -168,12 +172,13 @@ __host__ __device__ constexpr int cfg_nw_tma_small(int k, int mode)
     return k <= 8 ? 20 : 16;
 }
 // TMA: at most 3 table groups per buffer, fewer (= more zero-table padding) when the table buffers
-// would not leave room for the stages of at least 8 consumer warps
-__host__ __device__ constexpr int cfg_tma_groups(int k, int bufs, int stage_rows)
+// would not leave room for the stages of `want_nw` warps (reconstruct doubles the tables: k = 7 as
+// 4+2+1 is 192 KB of tables and 8 warps, as one padded group of 8 it is 64 KB and 28 warps)
+__host__ __device__ constexpr int cfg_tma_groups(int k, int bufs, int stage_rows, int want_nw)
 {
     for (int g = 3; g > 1; g--) {
         const TabLayout L = make_layout(k, 5, g);
-        if ((uint32_t)bufs * L.ngroups * kGroupBytes + kAuxBytes + 8u * stage_rows * kStageRowBytes <= kSmemLimit) return g;
+        if ((uint32_t)bufs * L.ngroups * kGroupBytes + kAuxBytes + (uint32_t)want_nw * stage_rows * kStageRowBytes <= kSmemLimit) return g;
     }
     return 1;
 }
@@ -211,7 +216,7 @@ template <int K, int MODE> struct StreamCfg {
     // <= 192 KB so that >= 32 KB stay L1 (round 1: 224 KB of tables starved the global loads).
     // TMA: groups of <= 32 tables, <= 3 groups per buffer; the loads bypass L1.
     static constexpr int kMaxLg = kTma ? 5 : GEC_LDG_MAXLG;
-    static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows) : 6 / kBufs;
+    static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows, K <= 12 ? 16 : 8) : 6 / kBufs;
     static constexpr TabLayout kLay = make_layout(K, kMaxLg, kMaxGrp);
     static constexpr int S = kLay.nslots;
     static constexpr uint32_t kTabBytes = (uint32_t)kBufs * kLay.ngroups * kGroupBytes;
@@ -284,7 +289,12 @@ struct ApplyParams {
     uint32_t row_off;           // first output row of this pass
     uint32_t items_per_stripe;  // ceil(ceil(stride/16)/32), uniform modes
     uint32_t row_bytes;         // 128: bytes per table row (a register operand keeps x*128 an IMAD)
+    uint32_t use_tmap;          // 1: `tmap` is valid (uniform modes, TMA path)
+    uint32_t rows_per_stripe;   // shards per stripe in `src` (k for encode, k+m for verify): tensor row of (s, j) = s*rows_per_stripe + j
     uint8_t coef[kRowsPerPass * kMaxK];  // uniform modes: coef[i*k + j]
+    // 2-D view of `src` for TMA: dim0 = stride/4 uint32 elements, dim1 = n*rows_per_stripe shards
+    // (pitch `stride`), box = 128 elements (512 B = 32 columns) x k rows
+    alignas(64) CUtensorMap tmap;
 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -371,6 +381,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// 2-D tiled TMA: box (128 uint32 x K rows) at element column c0, row c1 of the tensor described by
+// `tmap` -> dst (row r at dst + r*512); completes 512*K bytes on `bar` (also when the box sticks
+// out of the tensor: out-of-bounds elements are filled with zeros and still counted)
+__device__ __forceinline__ void tensor_g2s_2d(uint32_t dst, const CUtensorMap *tmap, uint32_t c0, uint32_t c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
 
@@ -694,18 +714,24 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
             z.sp = p.src + (unsigned long long)z.s * p.src_pitch + (size_t)z.col * 16;
             return z;
         };
-        // TMA: arm the stage and issue one bulk copy per staged row (lane 0)
+        // TMA: arm the stage and bring in the staged rows (lane 0): one 2-D tensor copy for the K source
+        // rows when the host supplied a tensor map, else one 1-D bulk copy per row
         auto issue = [&](const Pos &z) {
             if (!z.any || lane != 0) return;  // lane 0's column is the first of the chunk
             constexpr int NR = CFG::kStageRows;
-            const uint32_t nrow = MODE == kModeVerify ? (uint32_t)K + p.rows : (uint32_t)K;
-            mbar_arrive_expect_tx(bar_stage, z.rb * nrow);
+            const uint32_t prow = MODE == kModeVerify ? p.rows : 0u;  // stored parity rows staged behind the sources
+            if (GEC_TMAP && p.use_tmap) {
+                mbar_arrive_expect_tx(bar_stage, kStageRowBytes * K + z.rb * prow);
+                tensor_g2s_2d(stage_addr, &p.tmap, (z.col >> 5) * (kStageRowBytes / 4), z.s * p.rows_per_stripe, bar_stage);
+            } else {
+                mbar_arrive_expect_tx(bar_stage, z.rb * ((uint32_t)K + prow));
 #pragma unroll
-            for (int j = 0; j < NR; j++) {
-                if (j < K) bulk_g2s(stage_addr + j * kStageRowBytes, z.sp + (size_t)j * p.stride, z.rb, bar_stage);
-                else if ((uint32_t)(j - K) < p.rows)
-                    bulk_g2s(stage_addr + j * kStageRowBytes, z.sp + (size_t)(j + p.row_off) * p.stride, z.rb, bar_stage);
+                for (int j = 0; j < K; j++) bulk_g2s(stage_addr + j * kStageRowBytes, z.sp + (size_t)j * p.stride, z.rb, bar_stage);
             }
+#pragma unroll
+            for (int j = K; j < NR; j++)
+                if ((uint32_t)(j - K) < prow)
+                    bulk_g2s(stage_addr + j * kStageRowBytes, z.sp + (size_t)(j + p.row_off) * p.stride, z.rb, bar_stage);
         };
         auto finish = [&](const Pos &z, const uint4 (&r)[4], const uint4 (&st)[4]) {
             uint32_t mm = 0;
@@ -1368,6 +1394,50 @@ __global__ void __launch_bounds__(kQuadThreads) blake2sum_shards_quad_kernel(con
         const unsigned long long e = *reinterpret_cast<const unsigned long long *>(q.expect + oi * 32 + 8 * c);
         const uint32_t diff = __ballot_sync(qmask, e != h0) & qmask;
         if (c == 0) q.bad[oi] = diff ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------ block -> shard framing on the device
+// rpc_put_block hands over a contiguous block (bytes::Bytes); the streaming kernels want k shards,
+// `stride` apart and 16-byte aligned, the last one zero padded (DataBlock::from_buffer framing,
+// src/block/block.rs:85-96; short last block src/api/s3/put.rs:583-617).  The block crosses PCIe as
+// ONE contiguous copy (a pitched 2-D copy with an odd row width -- shard_len is rarely a multiple of
+// 16 -- runs far below the link rate) and this kernel cuts it up at HBM speed: every thread
+// produces one 16-byte vector of one shard from an arbitrarily aligned source position (five
+// aligned 32-bit loads + funnel shifts), zero beyond the shard / the block.
+struct SplitParams {
+    const uint8_t *blocks;       // block s at blocks + s*block_pitch (16-byte aligned)
+    const uint32_t *block_len;   // per block
+    uint8_t *shards;             // shard j of block s at shards + (s*k + j)*stride
+    unsigned long long block_pitch;
+    uint32_t stride, k, n;
+};
+__global__ void __launch_bounds__(256) split_blocks_kernel(const __grid_constant__ SplitParams q)
+{
+    for (uint32_t s = blockIdx.x; s < q.n; s += gridDim.x) {
+        const uint32_t len = __ldg(q.block_len + s);
+        const uint32_t L = (len + q.k - 1) / q.k, nvec = (L + 15) >> 4;
+        const uint8_t *src = q.blocks + (unsigned long long)s * q.block_pitch;
+        uint8_t *dst = q.shards + (unsigned long long)s * q.k * q.stride;
+        for (uint32_t idx = threadIdx.x; idx < q.k * nvec; idx += blockDim.x) {
+            const uint32_t j = idx / nvec, v = idx - j * nvec;
+            const uint32_t pos = j * L + v * 16;  // first source byte of this vector
+            // valid bytes: inside the shard and inside the block
+            uint32_t nvalid = min(16u, L - v * 16);
+            nvalid = pos >= len ? 0 : min(nvalid, len - pos);
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (nvalid) {
+                const uint32_t a = pos & ~3u, sh = (pos & 3u) * 8;
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(src + a);
+                // words a .. a+16 hold bytes pos .. pos+15 (+ up to 3 on either side); the staging buffer is
+                // padded so that reading one word past the block is always inside the allocation
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0;
+                o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                               __funnelshift_r(w3, w4, sh));
+                if (nvalid < 16) o = mask_tail(o, nvalid);
+            }
+            *reinterpret_cast<uint4 *>(dst + (size_t)j * q.stride + (size_t)v * 16) = o;
+        }
     }
 }
 

@@ -21,6 +21,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--erasures", type=int, default=None)
 ap.add_argument("--same-pattern", action="store_true", help="all stripes lose the same shards")
 ap.add_argument("--tag", default="")
+ap.add_argument("--stride-pad", type=int, default=0, help="extra bytes between shards (multiple of 16)")
 args = ap.parse_args()
 
 from garage_b200 import _build  # noqa: E402
@@ -38,7 +39,7 @@ e = args.erasures if args.erasures is not None else m
 B = 1 << 20
 ec = G.GarageEc(0, k, m)
 L = ec.shard_len(B)
-stride = ec.stride_for(L)
+stride = ec.stride_for(L) + args.stride_pad
 shards = torch.zeros(n * tot * stride, dtype=torch.uint8, device="cuda")
 sh3 = shards.view(n, tot, stride)
 data = torch.empty(n * k * stride, dtype=torch.uint8, device="cuda")
