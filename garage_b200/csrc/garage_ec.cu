@@ -354,7 +354,7 @@ int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pit
             p.items_per_stripe = ips;
             p.row_bytes = 128;
             p.rows_per_stripe = (uint32_t)(src_pitch / stride);
-            p.use_tmap = make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe, ctx->k) ? 1u : 0u;
+            p.use_tmap = (GEC_TMAP && ctx->k >= GEC_TMAP_FROM_K && make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe, ctx->k)) ? 1u : 0u;
             for (uint32_t i = 0; i < p.rows; i++)
                 memcpy(p.coef + i * ctx->k, ctx->P + (r0 + i) * ctx->k, ctx->k);
             cudaError_t e = mode == kModeEncode ? launch_apply<kModeEncode>(ctx, p, st)

@@ -73,9 +73,14 @@ namespace garage_ec {
 #ifndef GEC_NW_VER
 #define GEC_NW_VER 0
 #endif
-#ifndef GEC_TMAP
-#define GEC_TMAP 1  // uniform modes, TMA path: ONE 2-D tensor copy (k rows x 512 B) per work item instead of k 1-D copies
+#ifndef GEC_TMAP_FROM_K
+// uniform modes, TMA path: ONE 2-D tensor copy (k rows x 512 B) per work item instead of k 1-D copies, from this k
+// on.  Measured (profiles/r02_kbench_tmap_and_large_k.log): the single copy saves ~7 issue slots per source row, which
+// is what matters for k >= 13 (encode RS(20,4) 0.82 -> 0.94, RS(24,4) 0.77 -> 1.03, verify RS(16,4) 0.93 -> 0.99),
+// but k <= 12 encode is faster with k independent 1-D copies in flight (RS(10,4) 1.015 vs 0.92).  0 = never.
+#define GEC_TMAP_FROM_K 13
 #endif
+#define GEC_TMAP (GEC_TMAP_FROM_K > 0)
 #ifndef GEC_LDG_MAXLG
 #define GEC_LDG_MAXLG 3  // LDG path: largest table group = 2^3 tables (64 contiguous bytes per shard and instruction)
 #endif
@@ -155,7 +160,7 @@ constexpr uint32_t kAuxBytes = 2 * sizeof(PlanSlot) + 8 * (4 + 32) + 64;  // pla
 // k = 4, 6, 8, 10, 12).
 __host__ __device__ constexpr bool cfg_default_tma(int k, int mode)
 {
-    if (mode == kModeVerify) return k > 6;  // verify: LDG with prefetch wins up to k = 6
+    if (mode == kModeVerify) return k == 4 || k > 6;  // verify: LDG with prefetch wins for k = 1..3, 5, 6
     return k >= GEC_TMA_FROM_K;
 }
 __host__ __device__ constexpr int cfg_nw_ldg(int k, int mode)
@@ -168,7 +173,7 @@ __host__ __device__ constexpr int cfg_nw_ldg(int k, int mode)
 __host__ __device__ constexpr int cfg_nw_tma_small(int k, int mode)
 {
     if (mode == kModePlan) return k <= 6 ? 32 : (k <= 8 ? 28 : 24);
-    if (mode == kModeVerify) return k <= 8 ? 20 : 16;
+    if (mode == kModeVerify) return k <= 4 ? 28 : (k <= 8 ? 20 : 16);
     return k <= 8 ? 20 : 16;
 }
 // TMA: at most 3 table groups per buffer, fewer (= more zero-table padding) when the table buffers
@@ -226,7 +231,9 @@ template <int K, int MODE> struct StreamCfg {
     static constexpr int kWarpsDefault =
         !kTma ? cfg_nw_ldg(K, MODE)
               : (K <= 12 ? cfg_fit_nw(cfg_nw_tma_small(K, MODE), kTabBytes, kStageRows, MODE == kModePlan)
-                         : cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows));
+                 : (K <= 16 && MODE == kModePlan)
+                     ? cfg_fit_nw(16, kTabBytes, kStageRows, true)  // sweep: RS(14,4) 0.81 -> 0.92, RS(16,4) 0.89 -> 0.95
+                     : cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows));
     // an override (tuning builds) is clamped to what the stage memory allows
     static constexpr int kWarpsAll =
         kNwOverride > 0 ? (kTma ? cfg_fit_nw(kNwOverride, kTabBytes, kStageRows, MODE == kModePlan) : kNwOverride) : kWarpsDefault;
@@ -720,7 +727,7 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
             if (!z.any || lane != 0) return;  // lane 0's column is the first of the chunk
             constexpr int NR = CFG::kStageRows;
             const uint32_t prow = MODE == kModeVerify ? p.rows : 0u;  // stored parity rows staged behind the sources
-            if (GEC_TMAP && p.use_tmap) {
+            if (GEC_TMAP && K >= GEC_TMAP_FROM_K && p.use_tmap) {
                 mbar_arrive_expect_tx(bar_stage, kStageRowBytes * K + z.rb * prow);
                 tensor_g2s_2d(stage_addr, &p.tmap, (z.col >> 5) * (kStageRowBytes / 4), z.s * p.rows_per_stripe, bar_stage);
             } else {

@@ -116,7 +116,7 @@ def test_block_level_host_fault(torch):
         sums = np.zeros(n * tot * 32, dtype=np.uint8)
         ec.encode_blocks(blocks, par, stride, sums_out=sums)
         good_par, good_sums = par.copy(), sums.copy()
-        for fail_at in (0, 3, 9, 40, 200):
+        for fail_at in (0, 3, 9, 14):
             ec.debug_fail_after(fail_at)
             with pytest.raises(G.EcError):
                 ec.encode_blocks(blocks, par, stride, sums_out=sums)
