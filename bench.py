@@ -706,7 +706,13 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
             bufs = []
             n //= 2
             if n < 64:
-                return {"value": None, "unit": "GiB/s", "error": "pinned allocation failed"}
+                break
+    if n < 64:  # no pinned memory on this rank: still take part in the collectives below, then report the failure
+        if world > 1:
+            dist.barrier()
+            dummy = torch.zeros(7, dtype=torch.float64, device=dev)
+            dist.all_gather([torch.zeros_like(dummy) for _ in range(world)], dummy)
+        return {"value": None, "unit": "GiB/s", "error": "pinned allocation failed on rank %d" % rank}
     torch.from_numpy(h_data).copy_(data_d[: n * k * stride])
     torch.from_numpy(h_sh).copy_(shards_d[: n * tot * stride])
     h_present = np.ascontiguousarray(present[:n].numpy())
@@ -739,7 +745,7 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     gpu_node, buf_node = enc.numa_info()
-    mine = torch.tensor([el, t_enc, t_dec, float(gpu_node), float(buf_node), float(len(os.sched_getaffinity(0)))],
+    mine = torch.tensor([el, t_enc, t_dec, float(gpu_node), float(buf_node), float(len(os.sched_getaffinity(0))), float(n)],
                         dtype=torch.float64, device=dev)
     if world > 1:
         allr = [torch.zeros_like(mine) for _ in range(world)]
@@ -747,7 +753,12 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
     else:
         allr = [mine]
     allr = [[float(x) for x in t.tolist()] for t in allr]
+    if any(r[6] <= 0 for r in allr):
+        for p in bufs:
+            enc.host_free(p)
+        return {"value": None, "unit": "GiB/s", "error": "pinned allocation failed on another rank"}
     el = max(r[0] for r in allr)
+    n_all = sum(int(r[6]) for r in allr)  # blocks per e2e step over all ranks (a rank short of pinned memory runs fewer)
     # the e2e results are the same bytes the device-resident pass produced (sampled stripes)
     ref = shards_d.view(-1, tot, stride)
     ok = not h_status.any()
@@ -759,7 +770,8 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
     up_enc, dn_enc = n * k * stride + n * 4, n * m * stride
     up_dec, dn_dec = n * k * stride + n * 4 + n * tot, n * m * ((L + 15) // 16 * 16) + n * 4
     res = {
-        "value": 2 * n * B * world * steps / el / GIB, "unit": "GiB/s", "steps": steps, "blocks_per_step": n,
+        "value": 2 * n_all * B * steps / el / GIB, "unit": "GiB/s", "steps": steps, "blocks_per_step": n,
+        "blocks_per_step_all_ranks": n_all,
         # whole job (all ranks): encode data + the k survivors up; parity + rebuilt shards + status down
         "h2d_bytes_per_step": int(world * (up_enc + up_dec)),
         "d2h_bytes_per_step": int(world * (dn_enc + dn_dec)),
@@ -767,7 +779,7 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
                "(NUMA-local to the GPU), calling thread bound to the GPU's node (garage_ec_bind_thread)",
         "timer": "host wall clock around synchronous calls (max over ranks)", "checked": bool(ok),
         # per-rank link numbers: which rank (which socket / root complex) limits the job
-        "per_rank": [{"rank": i, "GiBs": 2 * n * B * steps / r[0] / GIB,
+        "per_rank": [{"rank": i, "GiBs": 2 * int(r[6]) * B * steps / r[0] / GIB,
                       "encode_h2d_GBs": up_enc * steps / r[1] / 1e9, "encode_d2h_GBs": dn_enc * steps / r[1] / 1e9,
                       "reconstruct_h2d_GBs": up_dec * steps / r[2] / 1e9, "reconstruct_d2h_GBs": dn_dec * steps / r[2] / 1e9,
                       "gpu_numa_node": int(r[3]), "pinned_buffer_numa_node": int(r[4]), "thread_affinity_cpus": int(r[5])}

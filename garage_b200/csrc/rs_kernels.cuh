@@ -81,6 +81,9 @@ namespace garage_ec {
 #define GEC_TMAP_FROM_K 13
 #endif
 #define GEC_TMAP (GEC_TMAP_FROM_K > 0)
+#ifndef GEC_SPLIT_STAGE
+#define GEC_SPLIT_STAGE 1
+#endif
 #ifndef GEC_LDG_MAXLG
 #define GEC_LDG_MAXLG 3  // LDG path: largest table group = 2^3 tables (64 contiguous bytes per shard and instruction)
 #endif
@@ -214,13 +217,17 @@ template <int K, int MODE> struct StreamCfg {
     static constexpr int kTmaOverride = MODE == kModeEncode ? GEC_TMA_ENC : (MODE == kModePlan ? GEC_TMA_PLAN : GEC_TMA_VER);
     static constexpr bool kTma = K > 16 || (kTmaOverride >= 0 ? (kTmaOverride != 0) : cfg_default_tma(K, MODE));
     static constexpr int kBufs = MODE == kModePlan ? 2 : 1;  // table buffers
-    static constexpr int kStageRows = kTma ? K + (MODE == kModeVerify ? kRowsPerPass : 0) : 0;
+    // reconstruct of k > 16: the stage holds ONE table group's rows (<= 16) at a time and an item is streamed
+    // in one phase per group -- with two table buffers a full k x 512 B stage per warp leaves room for only
+    // 7 consumer warps (RS(20,4) reconstruct 0.69 of peak)
+    static constexpr bool kSplit = kTma && MODE == kModePlan && K > 16 && GEC_SPLIT_STAGE;
+    static constexpr int kStageRows = kSplit ? 16 : (kTma ? K + (MODE == kModeVerify ? kRowsPerPass : 0) : 0);
     static constexpr int kNwOverride = MODE == kModeEncode ? GEC_NW_ENC : (MODE == kModePlan ? GEC_NW_PLAN : GEC_NW_VER);
 
     // LDG: groups of <= 8 tables (>= 64 contiguous bytes per shard and warp instruction), tables
     // <= 192 KB so that >= 32 KB stay L1 (round 1: 224 KB of tables starved the global loads).
     // TMA: groups of <= 32 tables, <= 3 groups per buffer; the loads bypass L1.
-    static constexpr int kMaxLg = kTma ? 5 : GEC_LDG_MAXLG;
+    static constexpr int kMaxLg = kSplit ? 4 : (kTma ? 5 : GEC_LDG_MAXLG);
     static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows, K <= 12 ? 16 : 8) : 6 / kBufs;
     static constexpr TabLayout kLay = make_layout(K, kMaxLg, kMaxGrp);
     static constexpr int S = kLay.nslots;
@@ -231,7 +238,7 @@ template <int K, int MODE> struct StreamCfg {
     static constexpr int kWarpsDefault =
         !kTma ? cfg_nw_ldg(K, MODE)
               : (K <= 12 ? cfg_fit_nw(cfg_nw_tma_small(K, MODE), kTabBytes, kStageRows, MODE == kModePlan)
-                 : (K <= 16 && MODE == kModePlan)
+                 : (MODE == kModePlan && (K <= 16 || kSplit))
                      ? cfg_fit_nw(16, kTabBytes, kStageRows, true)  // sweep: RS(14,4) 0.81 -> 0.92, RS(16,4) 0.89 -> 0.95
                      : cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows));
     // an override (tuning builds) is clamped to what the stage memory allows
@@ -660,6 +667,45 @@ __device__ __forceinline__ void column_compute(uint4 (&d)[CFG::S], uint32_t tab_
     rows_from_acc(acc, r);
 }
 
+// ---- one table group at a time (split staging): rows of group g sit at stage rows 0..size-1
+template <class CFG, int G>
+__device__ __forceinline__ void group_read(uint32_t stage_lane_addr, uint32_t lane, uint4 (&d)[16])
+{
+    constexpr TabLayout LAY = CFG::kLay;
+    constexpr int lg = LAY.lg[G], n = 1 << lg;
+    static_for<0, n>([&](auto pc) {
+        constexpr int ph = decltype(pc)::value;
+        const uint32_t row = (uint32_t)ph ^ (lg ? (lane >> (5 - lg)) : 0u);  // source base + row
+        if (LAY.base[G] + n <= (int)CFG::kK || (uint32_t)LAY.base[G] + row < (uint32_t)CFG::kK)
+            d[ph] = lds_v4(stage_lane_addr + row * kStageRowBytes);
+        else d[ph] = make_uint4(0, 0, 0, 0);
+    });
+}
+template <class CFG, int G>
+__device__ __forceinline__ void group_lookup(uint32_t (&acc)[16], uint4 (&d)[16], uint32_t tab_addr, uint32_t lane,
+                                             uint32_t row_bytes, uint32_t tail_bytes)
+{
+    constexpr TabLayout LAY = CFG::kLay;
+    constexpr int lg = LAY.lg[G], n = 1 << lg;
+    if (tail_bytes) {
+#pragma unroll
+        for (int u = 0; u < n; u++) d[u] = mask_tail(d[u], tail_bytes);
+    }
+    auto base_of = [&](int ph) -> uint32_t {
+        return tab_addr + (uint32_t)G * kGroupBytes + ((lane ^ ((uint32_t)ph << (lg ? 5 - lg : 0))) << 2);
+    };
+    if constexpr (n == 1) {
+        if (G == 0) lookup16<true>(acc, d[0], base_of(0), row_bytes);
+        else lookup16<false>(acc, d[0], base_of(0), row_bytes);
+    } else {
+        static_for<0, n / 2>([&](auto pc) {
+            constexpr int u = 2 * decltype(pc)::value;
+            if (G == 0 && u == 0) lookup16x2<true>(acc, d[u], base_of(u), d[u + 1], base_of(u + 1), row_bytes);
+            else lookup16x2<false>(acc, d[u], base_of(u), d[u + 1], base_of(u + 1), row_bytes);
+        });
+    }
+}
+
 // ------------------------------------------------------------------ the streaming kernel
 template <int K, int MODE> struct KernelCfg : StreamCfg<K, MODE> {
     static constexpr int kK = K;
@@ -948,10 +994,27 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
         };
         // start bringing in the columns of an item: TMA copies into the stage / LDG into dn
         uint4 dn[TMA ? 1 : S];
+        // split staging: rows of table group g only (stage row r = source base_g + r)
+        auto fetch_group = [&](const It &it, auto gc) {
+            constexpr int g = decltype(gc)::value;
+            constexpr TabLayout LAY = CFG::kLay;
+            constexpr int nrow = (LAY.base[g] + (1 << LAY.lg[g]) <= K) ? (1 << LAY.lg[g]) : (K - LAY.base[g]);
+            if (lane == 0) {
+                const PlanSlot &ps = slot[it.seq & 1];
+                const uint8_t *sbase = p.src + (unsigned long long)it.s * p.src_pitch + (size_t)it.chunk * kStageRowBytes;
+                const uint32_t rb = min(kStageRowBytes, (it.nvec - it.chunk * 32) * 16);
+                mbar_arrive_expect_tx(bar_stage, rb * nrow);
+#pragma unroll
+                for (int r = 0; r < nrow; r++)
+                    bulk_g2s(stage_addr + r * kStageRowBytes, sbase + ps.src_off[LAY.base[g] + r], rb, bar_stage);
+            }
+        };
         auto fetch = [&](const It &it) {
             const PlanSlot &ps = slot[it.seq & 1];
             const uint8_t *sbase = p.src + (unsigned long long)it.s * p.src_pitch;
-            if constexpr (TMA) {
+            if constexpr (CFG::kSplit) {
+                fetch_group(it, std::integral_constant<int, 0>{});
+            } else if constexpr (TMA) {
                 if (lane == 0) {
                     const uint32_t rb = min(kStageRowBytes, (it.nvec - it.chunk * 32) * 16);
                     mbar_arrive_expect_tx(bar_stage, rb * K);
@@ -969,6 +1032,48 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
         It nx;
         find(kNone, nx);
         if (nx.valid) fetch(nx);
+        if constexpr (CFG::kSplit) {
+            constexpr int NG = CFG::kLay.ngroups;
+            while (nx.valid) {
+                const It cur = nx;
+                const uint32_t col = cur.chunk * 32 + lane;
+                const bool have_col = col < cur.nvec;
+                const uint32_t tail = (have_col && col == cur.nvec - 1) ? (cur.len & 15) : 0;
+                uint32_t acc[16];
+                static_for<0, NG>([&](auto gc) {
+                    constexpr int g = decltype(gc)::value;
+                    uint4 d[16];
+                    mbar_wait(bar_stage, stage_parity);
+                    stage_parity ^= 1;
+                    group_read<CFG, g>(stage_addr + lane * 16, lane, d);
+                    __syncwarp();  // every lane has its vectors: the stage may be refilled
+                    if constexpr (g + 1 < NG) {
+                        fetch_group(cur, std::integral_constant<int, g + 1>{});  // next group of the same item
+                    } else {
+                        pend = cur.seq;
+                        find(cur.seq + 1, nx);
+                        if (nx.valid) fetch(nx);  // first group of the next item
+                    }
+                    if (have_col) group_lookup<CFG, g>(acc, d, tab_addr + (cur.seq & 1) * kTabBuf, lane, p.row_bytes, tail);
+                });
+                if (have_col) {
+                    const PlanSlot &ps = slot[cur.seq & 1];
+                    uint4 r[4];
+                    rows_from_acc(acc, r);
+                    uint8_t *dbase = p.dst + (unsigned long long)cur.s * p.dst_pitch;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < cur.rows) stg_stream(dbase + ps.dst_off[i] + (size_t)col * 16, r[i]);
+                }
+                if (pos != cur.seq) leave(cur.seq);
+                pend = kNone;
+                if (!nx.valid && !ended) {
+                    find(kNone, nx);
+                    if (nx.valid) fetch(nx);
+                }
+            }
+            return;
+        }
         while (nx.valid) {
             const It cur = nx;
             uint4 d[S];

@@ -33,7 +33,9 @@
  *   shard_len   per-stripe valid bytes per shard (NULL = `stride` for every stripe).
  *               Bytes in [shard_len, roundup16(shard_len)) of every OUTPUT shard are
  *               written as zero; input bytes there are ignored.  Beyond roundup16 nothing
- *               is read or written.
+ *               is written; input bytes up to `stride` may be read (the tile loads of the
+ *               k >= 13 kernels fetch whole 512-byte rows) but never influence a result,
+ *               so the whole n * shards * stride array must be addressable.
  *   all base pointers 16-byte aligned.
  */
 #ifndef GARAGE_EC_H
