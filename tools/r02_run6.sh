@@ -4,7 +4,8 @@ O=gpurun_out; V=build/variants
 timeout 900 python -m pytest tests -x -q -m gpu > $O/r02_r6_pytest.log 2>&1; echo "rc=$?" >> $O/r02_r6_pytest.log
 S=$O/r02_r6_sweep.log; : > $S
 kb() { timeout 120 python tools/kbench.py "$@" >> $S 2>&1; }
-for km in "10 4" "6 3" "4 2" "8 3" "12 4" "7 3" "14 4" "16 4" "17 4" "28 4" "32 4"; do set -- $km; kb --k $1 --m $2 --tag default; done
+for km in "10 4" "6 3" "4 2" "8 3" "12 4" "7 3" "14 4" "16 4" "17 4" "20 4" "24 4" "28 4" "32 4" "32 8"; do set -- $km; kb --k $1 --m $2 --tag default; done
+kb --so $V/libgarage_ec_ns20.so --k 20 --m 4 --tag nosplit; kb --so $V/libgarage_ec_ns32.so --k 32 --m 4 --tag nosplit
 for v in b7_ldg b7_nw16 b7_nw20 b7_nw24; do kb --so $V/libgarage_ec_$v.so --k 7 --m 3 --tag $v; done
 grep -h '^{' $S | python -c "
 import sys, json
