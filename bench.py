@@ -433,6 +433,7 @@ def run_ours(args, rank, world, local_rank):
     check_results("eager pass")
     # ---- scrub-verify of the same stripes (third streaming kernel; not part of the step): K launches
     mm = torch.zeros(n, dtype=torch.int32, device=dev)
+    time.sleep(1.0)  # same pause + fresh warm-up as before the eager pass (clocks sag after sustained load)
     for _ in range(3):
         enc.verify(shards, mm, stride, n, shard_len=lens)
     barrier()

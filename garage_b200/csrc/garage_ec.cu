@@ -308,20 +308,20 @@ TensorMapEncodeFn tensor_map_encoder()
 }
 // 2-D view of a shard array for the TMA path of the uniform kernels: dim0 = stride/4 uint32, dim1 = rows shards.
 // false = no tensor map (the kernel then issues one 1-D bulk copy per row)
-bool make_src_tensor_map(CUtensorMap *tm, const uint8_t *src, size_t stride, size_t rows, int k)
+bool make_src_tensor_map(CUtensorMap *tm, const uint8_t *src, size_t stride, size_t rows, int box_rows)
 {
 #if GEC_TMAP
     TensorMapEncodeFn enc = tensor_map_encoder();
-    if (!enc || stride < kStageRowBytes || rows == 0 || rows > 0xffffffffull || k > 256) return false;
+    if (!enc || stride < kStageRowBytes || rows == 0 || rows > 0xffffffffull || box_rows > 256) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)(stride / 4), (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)stride};
-    const cuuint32_t box[2] = {kStageRowBytes / 4, (cuuint32_t)k};
+    const cuuint32_t box[2] = {kStageRowBytes / 4, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(src), gdim, gstride, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 #else
-    (void)tm, (void)src, (void)stride, (void)rows, (void)k;
+    (void)tm, (void)src, (void)stride, (void)rows, (void)box_rows;
     return false;
 #endif
 }
@@ -354,7 +354,8 @@ int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pit
             p.items_per_stripe = ips;
             p.row_bytes = 128;
             p.rows_per_stripe = (uint32_t)(src_pitch / stride);
-            p.use_tmap = (GEC_TMAP && ctx->k >= GEC_TMAP_FROM_K && make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe, ctx->k)) ? 1u : 0u;
+            p.use_tmap = (GEC_TMAP && ctx->k >= GEC_TMAP_FROM_K && make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe,
+                                              (GEC_SPLIT_STAGE && ctx->k > 16) ? 16 : ctx->k)) ? 1u : 0u;  // box rows: StreamCfg::kSrcRows
             for (uint32_t i = 0; i < p.rows; i++)
                 memcpy(p.coef + i * ctx->k, ctx->P + (r0 + i) * ctx->k, ctx->k);
             cudaError_t e = mode == kModeEncode ? launch_apply<kModeEncode>(ctx, p, st)

@@ -164,6 +164,9 @@ constexpr uint32_t kAuxBytes = 2 * sizeof(PlanSlot) + 8 * (4 + 32) + 64;  // pla
 __host__ __device__ constexpr bool cfg_default_tma(int k, int mode)
 {
     if (mode == kModeVerify) return k == 4 || k > 6;  // verify: LDG with prefetch wins for k = 1..3, 5, 6
+    // reconstruct of k = 7 (4+2+1: three table groups, 192 KB for two buffers): LDG 0.95 of peak, TMA with one
+    // padded group of 8 and 27 warps 0.79 (profiles/r02_kbench_final.log)
+    if (mode == kModePlan && k == 7) return false;
     return k >= GEC_TMA_FROM_K;
 }
 __host__ __device__ constexpr int cfg_nw_ldg(int k, int mode)
@@ -220,8 +223,10 @@ template <int K, int MODE> struct StreamCfg {
     // reconstruct of k > 16: the stage holds ONE table group's rows (<= 16) at a time and an item is streamed
     // in one phase per group -- with two table buffers a full k x 512 B stage per warp leaves room for only
     // 7 consumer warps (RS(20,4) reconstruct 0.69 of peak)
-    static constexpr bool kSplit = kTma && MODE == kModePlan && K > 16 && GEC_SPLIT_STAGE;
-    static constexpr int kStageRows = kSplit ? 16 : (kTma ? K + (MODE == kModeVerify ? kRowsPerPass : 0) : 0);
+    // (the same for encode / verify of k > 16: reading all k vectors of a column into registers at once spills)
+    static constexpr bool kSplit = kTma && K > 16 && GEC_SPLIT_STAGE;
+    static constexpr int kSrcRows = kSplit ? 16 : K;  // source rows of a stage; stored parity rows (verify) follow
+    static constexpr int kStageRows = kTma ? kSrcRows + (MODE == kModeVerify ? kRowsPerPass : 0) : 0;
     static constexpr int kNwOverride = MODE == kModeEncode ? GEC_NW_ENC : (MODE == kModePlan ? GEC_NW_PLAN : GEC_NW_VER);
 
     // LDG: groups of <= 8 tables (>= 64 contiguous bytes per shard and warp instruction), tables
@@ -240,7 +245,7 @@ template <int K, int MODE> struct StreamCfg {
               : (K <= 12 ? cfg_fit_nw(cfg_nw_tma_small(K, MODE), kTabBytes, kStageRows, MODE == kModePlan)
                  : (MODE == kModePlan && (K <= 16 || kSplit))
                      ? cfg_fit_nw(16, kTabBytes, kStageRows, true)  // sweep: RS(14,4) 0.81 -> 0.92, RS(16,4) 0.89 -> 0.95
-                     : cfg_nw_tma(4 * S + 76, kTabBytes, kStageRows));
+                     : cfg_nw_tma(4 * (kSplit ? 16 : S) + 76, kTabBytes, kStageRows));
     // an override (tuning builds) is clamped to what the stage memory allows
     static constexpr int kWarpsAll =
         kNwOverride > 0 ? (kTma ? cfg_fit_nw(kNwOverride, kTabBytes, kStageRows, MODE == kModePlan) : kNwOverride) : kWarpsDefault;
@@ -819,14 +824,84 @@ __global__ void __launch_bounds__(StreamCfg<K, MODE>::kThreads, 1) rs_apply_kern
             for (int i = 0; i < 4; i++) {
                 st[i] = make_uint4(0, 0, 0, 0);
                 if (i < (int)p.rows && z.valid) {
-                    if (TMA) st[i] = lds_v4(stage_addr + lane * 16 + (K + i) * kStageRowBytes);
+                    if (TMA) st[i] = lds_v4(stage_addr + lane * 16 + (CFG::kSrcRows + i) * kStageRowBytes);
                     else st[i] = ldg_stream(z.sp + (size_t)(K + p.row_off + i) * p.stride);
                 }
             }
         };
 
         uint32_t item = blockIdx.x * NW + warp;
-        if constexpr (TMA) {
+        if constexpr (CFG::kSplit) {
+            // k > 16: one table group (<= 16 sources) per phase; the stage is refilled with the next group
+            // (or the first group of the next item) as soon as the current one sits in registers
+            constexpr TabLayout LAY = CFG::kLay;
+            constexpr int NG = LAY.ngroups;
+            auto issue_g = [&](const Pos &z, auto gc) {
+                constexpr int g = decltype(gc)::value;
+                constexpr int nrow = (LAY.base[g] + (1 << LAY.lg[g]) <= K) ? (1 << LAY.lg[g]) : (K - LAY.base[g]);
+                if (!z.any || lane != 0) return;
+                const uint32_t prow = (MODE == kModeVerify && g == NG - 1) ? p.rows : 0u;  // stored parity rides with the last group
+                if (GEC_TMAP && p.use_tmap) {
+                    // box = 16 rows: rows past this group are the next sources (or zero fill at the end of the
+                    // tensor); they are fetched and ignored
+                    mbar_arrive_expect_tx(bar_stage, kStageRowBytes * 16 + z.rb * prow);
+                    tensor_g2s_2d(stage_addr, &p.tmap, (z.col >> 5) * (kStageRowBytes / 4),
+                                  z.s * p.rows_per_stripe + LAY.base[g], bar_stage);
+                } else {
+                    mbar_arrive_expect_tx(bar_stage, z.rb * ((uint32_t)nrow + prow));
+#pragma unroll 1  // fallback path (no tensor map: stride < 512 B): keep it out of the register budget
+                    for (int r = 0; r < nrow; r++)
+                        bulk_g2s(stage_addr + r * kStageRowBytes, z.sp + (size_t)(LAY.base[g] + r) * p.stride, z.rb, bar_stage);
+                }
+#pragma unroll 1
+                for (uint32_t i = 0; i < prow; i++)
+                    bulk_g2s(stage_addr + (CFG::kSrcRows + i) * kStageRowBytes, z.sp + (size_t)(K + p.row_off + i) * p.stride, z.rb,
+                             bar_stage);
+            };
+            Pos nx;
+            nx.valid = nx.any = false;
+            if (item < total) {
+                nx = locate(item);
+                issue_g(nx, std::integral_constant<int, 0>{});
+            }
+            while (item < total) {
+                const Pos cur = nx;
+                if (!cur.any) {  // chunk past the end of a short stripe: nothing was staged for it
+                    item += gwarps;
+                    nx.valid = nx.any = false;
+                    if (item < total) {
+                        nx = locate(item);
+                        issue_g(nx, std::integral_constant<int, 0>{});
+                    }
+                    continue;
+                }
+                uint32_t acc[16];
+                uint4 st[4];
+                static_for<0, NG>([&](auto gc) {
+                    constexpr int g = decltype(gc)::value;
+                    uint4 d[16];
+                    mbar_wait(bar_stage, stage_parity);
+                    stage_parity ^= 1;
+                    group_read<CFG, g>(stage_addr + lane * 16, lane, d);
+                    if (g == NG - 1) load_stored(cur, st);
+                    __syncwarp();  // every lane has its vectors: the stage may be refilled
+                    if constexpr (g + 1 < NG) {
+                        issue_g(cur, std::integral_constant<int, g + 1>{});
+                    } else {
+                        item += gwarps;
+                        nx.valid = nx.any = false;
+                        if (item < total) {
+                            nx = locate(item);
+                            issue_g(nx, std::integral_constant<int, 0>{});
+                        }
+                    }
+                    if (cur.valid) group_lookup<CFG, g>(acc, d, tab_addr, lane, p.row_bytes, cur.tail);
+                });
+                uint4 r[4];
+                if (cur.valid) rows_from_acc(acc, r);
+                finish(cur, r, st);
+            }
+        } else if constexpr (TMA) {
             Pos nx;
             nx.valid = nx.any = false;
             if (item < total) {

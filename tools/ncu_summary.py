@@ -39,6 +39,28 @@ def one(path):
     return d
 
 
+def _bytes(txt):
+    """'4.299205 Gbyte' -> bytes"""
+    v, u = txt.split()[:2]
+    mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+    return float(v) * mul
+
+
+def traffic_json(summary_path, out_path, blocks, note):
+    """profiles/dominant_kernel_traffic.json (read by bench.py): dram read+write bytes per launch of the three
+    streaming kernels from captures named encode / reconstruct / verify in a summary written by this tool"""
+    d = json.load(open(summary_path))
+    res = {"note": note, "source": summary_path, "kernels": {}}
+    for name in ("encode", "reconstruct", "verify"):
+        if name in d:
+            r, w = _bytes(d[name]["dram__bytes_read.sum"]), _bytes(d[name]["dram__bytes_write.sum"])
+            res["kernels"][name] = {"dram_bytes_per_launch": r + w, "dram_bytes_read": r, "dram_bytes_write": w,
+                                    "blocks": blocks, "kernel": d[name]["Kernel Name"],
+                                    "gpu_time_under_ncu": d[name].get("gpu__time_duration.sum")}
+    json.dump(res, open(out_path, "w"), indent=1)
+    return res
+
+
 if __name__ == "__main__":
     res = {}
     for spec in sys.argv[2:]:

@@ -1,12 +1,11 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 O=gpurun_out; V=build/variants
-timeout 900 python -m pytest tests -x -q -m gpu > $O/r02_r6_pytest.log 2>&1; echo "rc=$?" >> $O/r02_r6_pytest.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_scrub_repair.py -x -q -m gpu > $O/r02_r6_pytest.log 2>&1; echo "rc=$?" >> $O/r02_r6_pytest.log
 S=$O/r02_r6_sweep.log; : > $S
 kb() { timeout 120 python tools/kbench.py "$@" >> $S 2>&1; }
-for km in "10 4" "6 3" "4 2" "8 3" "12 4" "7 3" "14 4" "16 4" "17 4" "20 4" "24 4" "28 4" "32 4" "32 8"; do set -- $km; kb --k $1 --m $2 --tag default; done
-kb --so $V/libgarage_ec_ns20.so --k 20 --m 4 --tag nosplit; kb --so $V/libgarage_ec_ns32.so --k 32 --m 4 --tag nosplit
-for v in b7_ldg b7_nw16 b7_nw20 b7_nw24; do kb --so $V/libgarage_ec_$v.so --k 7 --m 3 --tag $v; done
+for km in "10 4" "6 3" "4 2" "8 3" "12 4" "7 3" "3 2" "5 2" "9 3" "11 4" "13 4" "14 4" "16 4" "17 4" "20 4" "24 4" "28 4" "32 4" "32 8" "17 8" "2 8"; do set -- $km; kb --k $1 --m $2 --tag default; done
+kb --k 10 --m 4 --erasures 1 --tag default_e1; kb --k 10 --m 4 --erasures 2 --tag default_e2; kb --k 10 --m 4 --erasures 1 --same-pattern --tag default_same1
 grep -h '^{' $S | python -c "
 import sys, json
 for l in sys.stdin:
@@ -19,7 +18,7 @@ NCU="ncu --set full --clock-control none --import-source on --kernel-name-base d
 for mode in 0 1 2; do
   timeout 300 $NCU -k "regex:rs_apply_kernel<\(int\)10, \(int\)$mode>" -o $O/r02_ncu_final_mode$mode python tools/kbench.py --k 10 --m 4 --blocks 4096 --iters 3 > $O/r02_ncu_final_mode$mode.log 2>&1
 done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-sweep > $O/r02_launches_bench.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:garage_ec -c 60 --csv --log-file $O/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-sweep > $O/r02_launches_bench.log 2>&1
 timeout 200 compute-sanitizer --tool memcheck python tools/sanitize_small.py > $O/r02_r6_memcheck.log 2>&1
 timeout 200 compute-sanitizer --tool racecheck python tools/sanitize_small.py > $O/r02_r6_racecheck.log 2>&1
 timeout 200 compute-sanitizer --tool synccheck python tools/sanitize_small.py > $O/r02_r6_synccheck.log 2>&1
