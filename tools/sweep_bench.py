@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--stripes", type=int, default=2048, help="stripes per code per GPU")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--p", type=float, default=0.10)
+ap.add_argument("--sum-kind", type=int, default=1, help="per-shard tag: 1 adler8 (default), 0 blake2sum")
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -38,6 +39,7 @@ total_payload, total_ms = 0, 0.0
 for (k, m) in ((6, 3), (10, 4)):
     tot = k + m
     ec = G.GarageEc(local, k, m)
+    ec.set_sum_kind(args.sum_kind)
     L = ec.shard_len(B)
     stride = ec.stride_for(L)
     data = torch.empty(n * k * stride, dtype=torch.uint8, device="cuda")
@@ -70,13 +72,26 @@ for (k, m) in ((6, 3), (10, 4)):
         if it:
             ms += ev0.elapsed_time(ev1)
     ms /= args.iters
+    # the tag pass alone (detect), same shards
+    tag_ms = 0.0
+    for it in range(args.iters + 1):
+        torch.cuda.synchronize()
+        ev0.record()
+        ec.check_sums(shards.view(-1), sums, bad, stride, n, tot, shard_len=lens)
+        ev1.record()
+        torch.cuda.synchronize()
+        if it:
+            tag_ms += ev0.elapsed_time(ev1)
+    tag_ms /= args.iters
+    ec.scrub_repair(shards.view(-1), sums, bad, stride, n, status=status, shard_len=lens)  # `bad` back to the sweep's flags
     nbad = hit.sum(dim=1)
     unrec = int((nbad > m).sum())
     assert torch.equal(bad.view(n, tot).bool(), hit)
     assert int((status != 0).sum()) == unrec
     ok = status == 0
     assert torch.equal(shards[ok], orig[ok])
-    res["rs%d_%d" % (k, m)] = {"stripes": n, "ms": round(ms, 3), "payload_GiBs": round(n * B / ms / 1e-3 / 2**30, 1),
+    res["rs%d_%d" % (k, m)] = {"stripes": n, "ms": round(ms, 3), "tag_pass_ms": round(tag_ms, 3),
+                               "tag_pass_GBs": round(n * tot * L / tag_ms / 1e6, 1), "payload_GiBs": round(n * B / ms / 1e-3 / 2**30, 1),
                                "corrupt_shards": int(hit.sum()), "stripes_healed": int(((nbad > 0) & (nbad <= m)).sum()),
                                "unrecoverable": unrec}
     total_payload += n * B
@@ -87,7 +102,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"workload": "config 5: mixed RS(6,3)/RS(10,4), p=%.2f corrupted shards, detect+reconstruct+rewrite" % args.p,
-                      "n_gpus": world, "sweep_GiBs": round(total_payload * world / (float(t.item()) * 1e-3) / 2**30, 1),
+                      "n_gpus": world, "sum_kind": "adler8" if args.sum_kind else "blake2sum", "sweep_GiBs": round(total_payload * world / (float(t.item()) * 1e-3) / 2**30, 1),
                       "detail": res}))
 if world > 1:
     dist.destroy_process_group()
