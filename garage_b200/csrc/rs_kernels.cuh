@@ -233,7 +233,9 @@ template <int K, int MODE> struct StreamCfg {
     // <= 192 KB so that >= 32 KB stay L1 (round 1: 224 KB of tables starved the global loads).
     // TMA: groups of <= 32 tables, <= 3 groups per buffer; the loads bypass L1.
     static constexpr int kMaxLg = kSplit ? 4 : (kTma ? 5 : GEC_LDG_MAXLG);
-    static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows, K <= 12 ? 16 : 8) : 6 / kBufs;
+    // split staging: at most two phases per item (RS(28,4) as 16+8+4 streamed at 0.67 of peak: the short last
+    // phase leaves the next item's copy no time to land; as 16+16 with 4 zero tables it runs like RS(32,4))
+    static constexpr int kMaxGrp = kSplit ? 2 : (kTma ? cfg_tma_groups(K, kBufs, kStageRows, K <= 12 ? 16 : 8) : 6 / kBufs);
     static constexpr TabLayout kLay = make_layout(K, kMaxLg, kMaxGrp);
     static constexpr int S = kLay.nslots;
     static constexpr uint32_t kTabBytes = (uint32_t)kBufs * kLay.ngroups * kGroupBytes;

@@ -17,6 +17,13 @@ ncu -i /tmp/ncu_adler8.ncu-rep --page raw --csv > $O/r02_ncu_adler8_raw.csv 2>/d
 timeout 300 python tools/sweep_bench.py > $O/r02_sweep_config5_adler8.json 2>&1; timeout 300 python tools/sweep_bench.py --sum-kind 0 > $O/r02_sweep_config5_blake2.json 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:garage_ec -c 60 --csv --log-file $O/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-sweep > $O/r02_launches_bench.log 2>&1
 ( timeout 200 compute-sanitizer --tool memcheck python tools/sanitize_small.py; timeout 200 compute-sanitizer --tool racecheck python tools/sanitize_small.py; timeout 200 compute-sanitizer --tool synccheck python tools/sanitize_small.py ) > $O/r02_compute_sanitizer.log 2>&1
+for km in "10 4" "6 3" "4 2" "17 4" "21 4" "25 4" "28 4" "32 4"; do set -- $km; timeout 120 python tools/kbench.py --k $1 --m $2 --tag final >> $O/r02_kbench_final_extra.log 2>&1; done
+grep -h '^{' $O/r02_kbench_final_extra.log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l)
+    print('%-8s k=%2d m=%d ok=%d enc %.3f dec %.3f ver %.3f' % (d['tag'], d['k'], d['m'], d['ok'], d['encode_frac'], d['decode_frac'], d['verify_frac']))
+"
 timeout 300 python tools/blocklat.py > $O/r02_blocklat.json 2>&1
 for t in 16 64 128; do timeout 300 python tools/bm_bench.py --threads $t --blocks $((2048/t)) >> $O/r02_bm.log 2>&1; done
 timeout 300 python tools/bm_bench.py --threads 128 --blocks 16 --no-verify >> $O/r02_bm.log 2>&1
