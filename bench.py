@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 scrub/repair sweep extra")
-    ap.add_argument("--sweep-stripes", type=int, default=1024, help="stripes per code per GPU in the sweep extra")
+    ap.add_argument("--sweep-stripes", type=int, default=4096, help="stripes per code per GPU in the sweep extra")
     ap.add_argument("--sweep-e2e-stripes", type=int, default=512,
                     help="stripes per code per GPU in the HOST-buffer (end-to-end) sweep companion")
     a = ap.parse_args()

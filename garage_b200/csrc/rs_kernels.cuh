@@ -233,9 +233,7 @@ template <int K, int MODE> struct StreamCfg {
     // <= 192 KB so that >= 32 KB stay L1 (round 1: 224 KB of tables starved the global loads).
     // TMA: groups of <= 32 tables, <= 3 groups per buffer; the loads bypass L1.
     static constexpr int kMaxLg = kSplit ? 4 : (kTma ? 5 : GEC_LDG_MAXLG);
-    // split staging: at most two phases per item (RS(28,4) as 16+8+4 streamed at 0.67 of peak: the short last
-    // phase leaves the next item's copy no time to land; as 16+16 with 4 zero tables it runs like RS(32,4))
-    static constexpr int kMaxGrp = kSplit ? 2 : (kTma ? cfg_tma_groups(K, kBufs, kStageRows, K <= 12 ? 16 : 8) : 6 / kBufs);
+    static constexpr int kMaxGrp = kTma ? cfg_tma_groups(K, kBufs, kStageRows, K <= 12 ? 16 : 8) : 6 / kBufs;
     static constexpr TabLayout kLay = make_layout(K, kMaxLg, kMaxGrp);
     static constexpr int S = kLay.nslots;
     static constexpr uint32_t kTabBytes = (uint32_t)kBufs * kLay.ngroups * kGroupBytes;
@@ -1648,43 +1646,48 @@ __host__ __device__ inline uint32_t adler8_seg_bytes(uint32_t len)
 
 __global__ void __launch_bounds__(256) adler8_shards_kernel(const __grid_constant__ SumParams q)
 {
+    // work unit = one SEGMENT of one shard per warp (8 units per shard): 8x the units of a warp-per-shard
+    // split, so the persistent grid stays balanced down to a few hundred shards (ncu of the warp-per-shard
+    // version: 50 % of DRAM peak with a 2-wave tail at 18 432 shards).  `bad` must be zero on entry when
+    // `expect` is given (the host memsets it): segments OR their verdict into the shard's flag byte.
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t wpb = blockDim.x >> 5;
-    for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < q.n_shards; i += gridDim.x * wpb) {
+    const uint32_t units = q.n_shards * 8u;  // host guarantees n_shards < 2^29
+    for (uint32_t u = blockIdx.x * wpb + (threadIdx.x >> 5); u < units; u += gridDim.x * wpb) {
+        const uint32_t i = u >> 3, sgi = u & 7;
         const uint8_t *p;
         uint32_t len;
         size_t oi;
         locate_shard(q, i, p, len, oi);
         const uint32_t seg = adler8_seg_bytes(len);
-        uint32_t mine = 1;  // lane s < 8 ends up with the Adler-32 of segment s
-        for (uint32_t sgi = 0; sgi < 8; sgi++) {
-            const uint32_t start = sgi * seg;
-            if (start >= len) break;  // this and all later segments are empty: Adler-32 = 1
+        const uint32_t start = sgi * seg;
+        uint32_t tag = 1;  // Adler-32 of an empty segment
+        if (start < len) {
             const uint32_t end = min(len, start + seg), n = end - start;
             unsigned long long A = 0, B = 0, T = 0;
-            // 4 vectors per lane in flight: rel = byte offset of the vector inside the segment
-            for (uint32_t r0 = lane * 16; r0 < n; r0 += 4 * 512) {
-                uint4 v[4];
+            // 8 vectors per lane in flight: rel = byte offset of the vector inside the segment
+            for (uint32_t r0 = lane * 16; r0 < n; r0 += 8 * 512) {
+                uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t rel = r0 + u * 512;
-                    v[u] = make_uint4(0, 0, 0, 0);
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t rel = r0 + k * 512;
+                    v[k] = make_uint4(0, 0, 0, 0);
                     if (rel < n) {
-                        v[u] = ldg_stream(p + start + rel);  // within roundup16(len): readable
-                        if (n - rel < 16) v[u] = mask_tail(v[u], n - rel);
+                        v[k] = ldg_stream(p + start + rel);  // within roundup16(len): readable
+                        if (n - rel < 16) v[k] = mask_tail(v[k], n - rel);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t rel = r0 + u * 512;
-                    uint32_t sm = __dp4a(v[u].x, 0x01010101u, 0u);
-                    sm = __dp4a(v[u].y, 0x01010101u, sm);
-                    sm = __dp4a(v[u].z, 0x01010101u, sm);
-                    sm = __dp4a(v[u].w, 0x01010101u, sm);
-                    uint32_t t = __dp4a(v[u].x, 0x03020100u, 0u);  // sum_j j * byte_j
-                    t = __dp4a(v[u].y, 0x07060504u, t);
-                    t = __dp4a(v[u].z, 0x0b0a0908u, t);
-                    t = __dp4a(v[u].w, 0x0f0e0d0cu, t);
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t rel = r0 + k * 512;
+                    uint32_t sm = __dp4a(v[k].x, 0x01010101u, 0u);
+                    sm = __dp4a(v[k].y, 0x01010101u, sm);
+                    sm = __dp4a(v[k].z, 0x01010101u, sm);
+                    sm = __dp4a(v[k].w, 0x01010101u, sm);
+                    uint32_t t = __dp4a(v[k].x, 0x03020100u, 0u);  // sum_j j * byte_j
+                    t = __dp4a(v[k].y, 0x07060504u, t);
+                    t = __dp4a(v[k].z, 0x0b0a0908u, t);
+                    t = __dp4a(v[k].w, 0x0f0e0d0cu, t);
                     A += sm;
                     if (rel < n) B += (unsigned long long)(n - rel) * sm;
                     T += t;
@@ -1698,13 +1701,15 @@ __global__ void __launch_bounds__(256) adler8_shards_kernel(const __grid_constan
             }
             const uint32_t a = (uint32_t)((1 + A) % kAdlerMod);
             const uint32_t b = (uint32_t)((n + B - T) % kAdlerMod);  // B >= T: (n - rel) >= j + 1 for every byte
-            if (lane == sgi) mine = (b << 16) | a;
+            tag = (b << 16) | a;
         }
-        if (q.sums && lane < 8) reinterpret_cast<uint32_t *>(q.sums + oi * 32)[lane] = mine;
-        if (q.expect && q.bad) {
-            const uint32_t e = lane < 8 ? reinterpret_cast<const uint32_t *>(q.expect + oi * 32)[lane] : 0;
-            const uint32_t diff = __ballot_sync(0xffffffffu, lane < 8 && e != mine);
-            if (lane == 0) q.bad[oi] = diff ? 1 : 0;
+        if (lane == 0) {
+            if (q.sums) reinterpret_cast<uint32_t *>(q.sums + oi * 32)[sgi] = tag;
+            if (q.expect && q.bad && reinterpret_cast<const uint32_t *>(q.expect + oi * 32)[sgi] != tag) {
+                // set byte `oi` of bad[] to 1 through the aligned 32-bit word that contains it
+                const unsigned long long addr = reinterpret_cast<unsigned long long>(q.bad + oi);
+                atomicOr(reinterpret_cast<unsigned int *>(addr & ~3ull), 1u << (8 * (unsigned)(addr & 3ull)));
+            }
         }
     }
 }
