@@ -567,6 +567,7 @@ struct garage_bm {
     int enc_next[kWorkers] = {0};
     PinnedBuf scrub_buf;
     std::mutex scrub_mu;
+    std::atomic<bool> warmed{false};
     // metrics (src/block/metrics.rs)
     std::atomic<uint64_t> bytes_written{0}, bytes_read{0}, corruption_counter{0}, resync_counter{0},
         resync_error_counter{0}, resync_recv_counter{0}, delete_counter{0}, put_calls{0}, reconstruct_calls{0},
@@ -1184,6 +1185,22 @@ struct garage_bm {
                 });
             for (auto &x : th) x.join();
         }
+        if (mode == 0 && !warmed.exchange(true)) {
+            // first use of this manager: one block through every dispatcher (streams, lane buffers, kernels)
+            std::vector<uint8_t> wblk(words * 8);
+            gen(nb, wblk.data());
+            Hash wh;
+            garage_ec_blake2sum(wblk.data(), block_len, wh.data());
+            std::vector<std::thread> wt;
+            for (int t = 0; t < 3 * kWorkers; t++)
+                wt.emplace_back([&] {
+                    try {
+                        rpc_put_block(wh, wblk.data(), block_len);
+                    } catch (...) {
+                    }
+                });
+            for (auto &x : wt) x.join();
+        }
         std::atomic<uint64_t> errs{0};
         std::atomic<int> ready{0};
         std::atomic<bool> go{false};
@@ -1305,6 +1322,9 @@ static int bm_create(garage_bm **out, const garage_bm_config *cfg)
         garage_ec_set_sum_kind(bm->enc_ctx[w], bm->sum_kind);
         garage_ec_set_sum_kind(bm->rec_ctx[w], bm->sum_kind);
         bm->enc_out[w][0].ctx = bm->enc_out[w][1].ctx = bm->enc_ctx[w];
+        // the pinned parity buffers at their final size now, not on the first large batch
+        const size_t out_bytes = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * ((size_t)m * bm->slot_stride + (size_t)(k + m) * 32);
+        if (!bm->enc_out[w][0].get(out_bytes) || !bm->enc_out[w][1].get(out_bytes)) return destroy_on_error(GARAGE_EC_E_NOMEM);
     }
     const size_t nslots = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * (garage_bm::kWorkers + 1);
     if (!bm->put_slots.init(bm->ec, nslots, bm->cfg.block_size)) return destroy_on_error(GARAGE_EC_E_NOMEM);

@@ -471,8 +471,15 @@ struct CopyBatch {
 };
 
 // ---- host lanes -----------------------------------------------------------------------
+// A lane's buffers are sized for a full pipeline chunk the first time they are needed (not for the
+// batch at hand): a batching front-end calls with a different number of blocks every time, and every
+// cudaFree + cudaMalloc to grow a lane synchronises the whole device -- with growth-on-demand the first few
+// hundred calls of a fresh context paid milliseconds each (profiles/r02_summary.md, block-manager bench)
+constexpr size_t kLaneFloorBytes = 128ull << 20, kLaneSmallFloorBytes = 2ull << 20;
 int lane_reserve(garage_ec_ctx *ctx, HostLane &L, size_t buf_bytes, size_t small_bytes)
 {
+    if (buf_bytes < kLaneFloorBytes) buf_bytes = kLaneFloorBytes;
+    if (small_bytes < kLaneSmallFloorBytes) small_bytes = kLaneSmallFloorBytes;
     if (!L.stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
     if (L.d_cap < buf_bytes) {
         if (L.d_buf) cudaFree(L.d_buf);
