@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "garage_ec_params", "garage_ec_strerror", "garage_ec_last_error", "garage_ec_abi_version",
     "garage_ec_shard_len", "garage_ec_stride_for", "garage_ec_encode", "garage_ec_reconstruct",
     "garage_ec_verify", "garage_ec_encode_blocks", "garage_ec_decode_blocks",
-    "garage_ec_fill_random", "garage_ec_host_alloc", "garage_ec_host_free",
+    "garage_ec_fill_random", "garage_ec_host_alloc", "garage_ec_host_alloc_wc", "garage_ec_host_free",
     "garage_ec_launch_count", "garage_ec_set_timing", "garage_ec_timing_read",
     "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
     "garage_ec_encode_blocks_with_sums", "garage_ec_scrub_repair",
@@ -96,6 +96,7 @@ def load_library(build=True):
     L.garage_ec_decode_blocks.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp]
     L.garage_ec_fill_random.argtypes = [vp, vp, sz, u64, u64, vp]
     L.garage_ec_host_alloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.garage_ec_host_alloc_wc.argtypes = [vp, C.POINTER(vp), sz]
     L.garage_ec_host_free.argtypes = [vp, vp]
     L.garage_ec_host_free.restype = None
     L.garage_ec_launch_count.argtypes = [vp]
@@ -300,10 +301,11 @@ class GarageEc:
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         return self._check(self._L.garage_ec_fill_random(self._h, _ptr(dst), nbytes, seed, offset, st))
 
-    def host_alloc(self, nbytes):
+    def host_alloc(self, nbytes, write_combined=False):
         """pinned host buffer as a numpy uint8 array (freed with host_free)."""
         p = C.c_void_p()
-        self._check(self._L.garage_ec_host_alloc(self._h, C.byref(p), nbytes))
+        fn = self._L.garage_ec_host_alloc_wc if write_combined else self._L.garage_ec_host_alloc
+        self._check(fn(self._h, C.byref(p), nbytes))
         arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
         return arr, p
 

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cctype>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,7 +68,10 @@ struct garage_ec_ctx {
     bool have_node_cpus = false;
     cpu_set_t node_cpus;
     int last_alloc_node = -1;                 // node the last garage_ec_host_alloc landed on (-1 unknown)
-    std::atomic<long> fault_countdown{-1};    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
+    std::atomic<long> fault_countdown{-1};
+    // GARAGE_EC_TRACE=1: host-side time per phase of the block-level encode call, printed at destroy (tuning aid)
+    bool trace = false;
+    std::atomic<uint64_t> tr_calls{0}, tr_blocks{0}, tr_prep_us{0}, tr_issue_us{0}, tr_sync_us{0};    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
     std::mutex misc_mu;  // timing list, last_error
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -532,6 +536,7 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
         return GARAGE_EC_E_NODEVICE;
     }
     probe_numa(ctx);
+    ctx->trace = getenv("GARAGE_EC_TRACE") != nullptr;
     *out = ctx;
     return GARAGE_EC_OK;
 }
@@ -580,6 +585,11 @@ int garage_ec_create_with_matrix(garage_ec_ctx **out, int cuda_device, int k, in
 void garage_ec_destroy(garage_ec_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->trace && ctx->tr_calls.load())
+        fprintf(stderr, "garage_ec trace ctx %p: encode_blocks calls=%llu blocks=%llu  per call: prep %.1f us, issue %.1f us, sync %.1f us\n",
+                (void *)ctx, (unsigned long long)ctx->tr_calls.load(), (unsigned long long)ctx->tr_blocks.load(),
+                (double)ctx->tr_prep_us.load() / ctx->tr_calls.load(), (double)ctx->tr_issue_us.load() / ctx->tr_calls.load(),
+                (double)ctx->tr_sync_us.load() / ctx->tr_calls.load());
     cudaSetDevice(ctx->device);
     for (LaneSet *set : ctx->free_sets) {
         for (HostLane &L : set->lanes) {
@@ -671,7 +681,16 @@ int garage_ec_timing_read(garage_ec_ctx *ctx, double *total_ms, uint64_t *launch
     return rc;
 }
 
-int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes)
+static int host_alloc_impl(garage_ec_ctx *ctx, void **out, size_t bytes, unsigned extra_flags);
+
+int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes) { return host_alloc_impl(ctx, out, bytes, 0); }
+
+int garage_ec_host_alloc_wc(garage_ec_ctx *ctx, void **out, size_t bytes)
+{
+    return host_alloc_impl(ctx, out, bytes, cudaHostAllocWriteCombined);
+}
+
+static int host_alloc_impl(garage_ec_ctx *ctx, void **out, size_t bytes, unsigned extra_flags)
 {
     if (!ctx || !out || !bytes) return GARAGE_EC_E_INVALID;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -693,7 +712,7 @@ int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes)
             if (CPU_COUNT(&want) > 0 && sched_setaffinity(0, sizeof(want), &want) == 0) moved = true;
         }
     }
-    cudaError_t e = fault_hit(ctx) ? cudaErrorMemoryAllocation : cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    cudaError_t e = fault_hit(ctx) ? cudaErrorMemoryAllocation : cudaHostAlloc(out, bytes, cudaHostAllocPortable | extra_flags);
     if (moved) sched_setaffinity(0, sizeof(saved_cpus), &saved_cpus);
     if (policy_set) syscall(SYS_set_mempolicy, MPOL_DEFAULT, nullptr, 0ul);
     if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaHostAlloc");
@@ -1264,6 +1283,7 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         if (garage_ec_shard_len(block_len[s], (int)k) > stride) return GARAGE_EC_E_INVALID;
         max_len = block_len[s] > max_len ? block_len[s] : max_len;
     }
+    const auto tr0 = std::chrono::steady_clock::now();
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     size_t cs = kHostChunkBytes / (k * stride);
     if (cs < 1) cs = 1;
@@ -1279,6 +1299,7 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         if (rc) return rc;
     }
     const size_t o_blen = cs * 4, o_sums = align_up(cs * 8, 16);
+    const auto tr1 = std::chrono::steady_clock::now();
     size_t c = 0;
     for (size_t s0 = 0; s0 < n_blocks; s0 += cs, c++) {
         const size_t lane_i = c % kHostLanes;
@@ -1323,7 +1344,17 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
                                         cudaMemcpyDeviceToHost, L.stream));
         }
     }
+    const auto tr2 = std::chrono::steady_clock::now();
     for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    if (ctx->trace) {
+        const auto tr3 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+        ctx->tr_calls++;
+        ctx->tr_blocks += n_blocks;
+        ctx->tr_prep_us += us(tr0, tr1);
+        ctx->tr_issue_us += us(tr1, tr2);
+        ctx->tr_sync_us += us(tr2, tr3);
+    }
     return GARAGE_EC_OK;
 }
 

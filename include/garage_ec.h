@@ -210,6 +210,10 @@ int garage_ec_fill_random(garage_ec_ctx *ctx, uint8_t *dst_device, size_t len, u
  * (BytesBuf::take_exact, src/net/bytes_buf.rs:66-117) directly in such a buffer so the DMA
  * engines can read it.  Pageable memory is accepted everywhere, only slower.               */
 int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes);
+/* same, write-combined (cudaHostAllocWriteCombined): for buffers the CPU only WRITES sequentially and the
+ * GPU reads (upload landing buffers) or the GPU writes and the CPU hands on without reading; CPU reads
+ * from such memory are very slow.  The pages are not snooped during DMA.                              */
+int garage_ec_host_alloc_wc(garage_ec_ctx *ctx, void **out, size_t bytes);
 void garage_ec_host_free(garage_ec_ctx *ctx, void *ptr);
 /* NUMA placement.  On a multi-socket host each GPU hangs off one socket; garage_ec_host_alloc
  * places its pages on that socket's memory node (preferred-node policy + first touch from a CPU

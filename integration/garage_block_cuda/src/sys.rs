@@ -62,6 +62,7 @@ extern "C" {
                             n_stripes: usize, mem_kind: c_int, cuda_stream: *mut c_void) -> c_int;
     pub fn garage_ec_blake2sum(data: *const u8, len: usize, out32: *mut u8);
     pub fn garage_ec_host_alloc(ctx: *mut garage_ec_ctx, out: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn garage_ec_host_alloc_wc(ctx: *mut garage_ec_ctx, out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn garage_ec_host_free(ctx: *mut garage_ec_ctx, ptr: *mut c_void);
     pub fn garage_ec_fill_random(ctx: *mut garage_ec_ctx, dst: *mut u8, len: usize, seed: u64,
                             offset: u64, cuda_stream: *mut c_void) -> c_int;

@@ -493,3 +493,54 @@ def test_device_calls_are_cuda_graph_capturable(torch):
             assert np.array_equal(host(par).reshape(n, m, stride), orig[:, k:])
             assert np.array_equal(host(sh).reshape(n, tot, stride), orig)
             assert not host(st).any() and not host(mm).any()
+
+
+# ------------------------------------------------------------------ every launch-shape class of k
+@pytest.mark.parametrize("k,m", [(5, 2), (7, 3), (9, 3), (11, 4), (14, 4), (15, 3), (16, 4), (19, 3), (20, 4), (21, 2),
+                                 (24, 3), (25, 2), (28, 4), (29, 4), (31, 1), (32, 4)])
+def test_every_table_layout_and_staging_class(torch, k, m):
+    """k selects the table-group layout (8+2, 16, 16+4, 16+8+4, 16+16 with padding ...), the staging path
+    (LDG / 1-D TMA / 2-D tensor map / split phases) and the warp count at compile time: encode, verify and
+    reconstruct of ragged stripes against the oracle for one k of every class, with strides on both sides of
+    the 512-byte tile (a stride < 512 B takes the fallback without a tensor map)."""
+    tot = k + m
+    for stride, lens in ((2048 + 16, [2064, 1, 17, 511, 512, 513, 1000, 2063]), (400, [400, 399, 16, 255])):
+        n = len(lens)
+        lens_a = np.array(lens, dtype=np.uint32)
+        data = O.fill_random(n * k * stride, 1000 * k + m + stride)
+        P = O.build_matrix(k, m, 0)
+        want = O.encode(k, m, P, data, stride, n, lens_a)
+        with G.GarageEc(0, k, m) as ec:
+            d = dev(torch, data)
+            dl = dev(torch, lens_a.astype(np.int32))
+            par = torch.full((n * m * stride,), 0xEE, dtype=torch.uint8, device="cuda")
+            ec.encode(d, par, stride, n, shard_len=dl)
+            got = host(par).reshape(n, m, stride)
+            w3 = want.reshape(n, m, stride)
+            for s in range(n):
+                Lp = (lens[s] + 15) // 16 * 16
+                assert np.array_equal(got[s, :, :lens[s]], w3[s, :, :lens[s]]), (k, m, stride, s)
+                assert not got[s, :, lens[s]:Lp].any() and (got[s, :, Lp:] == 0xEE).all()
+            sh = np.concatenate([data.reshape(n, k, stride), w3], axis=1)
+            mm = torch.ones(n, dtype=torch.int32, device="cuda")
+            ec.verify(dev(torch, sh.reshape(-1)), mm, stride, n, shard_len=dl)
+            assert int(mm.abs().sum()) == 0
+            hurt = sh.copy()
+            hurt[0, k, 0] ^= 1
+            hurt[n - 1, k + m - 1, lens[n - 1] - 1] ^= 0x80
+            ec.verify(dev(torch, hurt.reshape(-1)), mm, stride, n, shard_len=dl)
+            mmh = host(mm)
+            assert mmh[0] == 1 and mmh[n - 1] == 1 << (m - 1) and np.count_nonzero(mmh) == 2
+            rng = np.random.default_rng(k * 100 + m)
+            present = np.ones((n, tot), dtype=np.uint8)
+            for s in range(n):
+                present[s, rng.choice(tot, int(rng.integers(1, m + 1)), replace=False)] = 0
+            broken = sh.copy()
+            broken[present == 0] = 0x77
+            bd = dev(torch, broken.reshape(-1))
+            st = torch.ones(n, dtype=torch.int32, device="cuda")
+            ec.reconstruct(bd, dev(torch, present), stride, n, status=st, shard_len=dl)
+            assert int(st.abs().sum()) == 0
+            rec = host(bd).reshape(n, tot, stride)
+            for s in range(n):
+                assert np.array_equal(rec[s, :, :lens[s]], sh[s, :, :lens[s]]), (k, m, stride, s)
