@@ -1329,6 +1329,33 @@ static int bm_create(garage_bm **out, const garage_bm_config *cfg)
     const size_t nslots = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * (garage_bm::kWorkers + 1);
     if (!bm->put_slots.init(bm->ec, nslots, bm->cfg.block_size)) return destroy_on_error(GARAGE_EC_E_NOMEM);
     if (!bm->stripe_slots.init(bm->ec, nslots, (size_t)bm->tot * bm->slot_stride)) return destroy_on_error(GARAGE_EC_E_NOMEM);
+    // Warm every dispatcher's context now: streams, lane buffers, and the first launch of each kernel (CUDA
+    // loads kernels lazily) cost tens of milliseconds that would otherwise land on the first real batches.
+    {
+        SlotLease blk(bm->put_slots), stripe(bm->stripe_slots);
+        const uint32_t wlen = bm->cfg.block_size;
+        memset(blk.p, 0x5a, wlen);
+        memset(stripe.p, 0, (size_t)bm->tot * bm->slot_stride);
+        for (int w = 0; w < garage_bm::kWorkers; w++) {
+            const uint8_t *ptrs[1] = {blk.p};
+            uint8_t *par = bm->enc_out[w][0].get(1);
+            rc = garage_ec_encode_blocks_with_sums(bm->enc_ctx[w], ptrs, &wlen, 1, par, par + (size_t)m * bm->slot_stride, bm->slot_stride);
+            if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
+            uint8_t present[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M], want[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
+            memset(present, 1, sizeof(present));
+            present[0] = 0;
+            want[0] = 1;
+            uint8_t *stripes[1] = {stripe.p};
+            const uint32_t slen = (uint32_t)bm->shard_len_of(wlen);
+            int32_t st = 0;
+            rc = garage_ec_reconstruct_stripes(bm->rec_ctx[w], stripes, present, want, &st, &slen, bm->slot_stride, 1);
+            if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
+        }
+        uint8_t bad1 = 0, exp1[32] = {0};
+        const uint32_t slen = (uint32_t)bm->shard_len_of(wlen);
+        rc = garage_ec_check_sums(bm->ec, stripe.p, exp1, &slen, bm->slot_stride, 1, 1, &bad1, GARAGE_EC_MEM_HOST, nullptr);
+        if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
+    }
     garage_bm *raw = bm.get();
     auto bind = [raw] { garage_ec_bind_thread(raw->ec); };
     bm->enc_batcher.reset(new Batcher<EncodeItem>(cfg->batch_max_blocks, cfg->batch_linger_us, garage_bm::kWorkers,

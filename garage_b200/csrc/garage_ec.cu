@@ -1038,7 +1038,7 @@ static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *ex
     // LSU-bound: measured 5.4 ms vs 7.6 ms at 18 432 shards and 6.0 vs 5.7 ms at 28 672);
     // from ~24 000 shards on one thread per shard keeps the schedulers busy enough
     if (ctx->sum_kind.load(std::memory_order_relaxed) == GARAGE_EC_SUM_ADLER8) {
-        // one warp per (shard, segment), 8 warps per block, persistent grid
+        // one block per (shard, segment), persistent grid of 8 blocks per SM
         if (n_shards >= (1u << 29)) return GARAGE_EC_E_INVALID;
         if (expect && bad) {
             // segments OR their verdict into the shard's flag: clear the flags of this launch first.  Flags of
@@ -1047,7 +1047,7 @@ static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *ex
             cudaError_t e0 = cudaMemsetAsync(bad, 0, nflags, st);
             if (e0 != cudaSuccess) return set_cuda_error(ctx, e0, "cudaMemsetAsync(bad)");
         }
-        const unsigned blocks = (unsigned)std::min<size_t>(n_shards, (size_t)ctx->sm_count * 8);
+        const unsigned blocks = (unsigned)std::min<size_t>(n_shards * 8, (size_t)ctx->sm_count * 8);
         adler8_shards_kernel<<<blocks, 256, 0, st>>>(q);
     } else if (n_shards < 24000)
         blake2sum_shards_quad_kernel<<<(unsigned)((n_shards + kQuadThreads / 4 - 1) / (kQuadThreads / 4)), kQuadThreads, 0,

@@ -60,6 +60,7 @@ for (k, m) in ((6, 3), (10, 4)):
     status = torch.zeros(n, dtype=torch.int32, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = 0.0
+    per_iter = []
     for it in range(args.iters + 1):
         shards.copy_(orig)
         sidx, iidx = torch.nonzero(hit, as_tuple=True)
@@ -71,6 +72,7 @@ for (k, m) in ((6, 3), (10, 4)):
         torch.cuda.synchronize()
         if it:
             ms += ev0.elapsed_time(ev1)
+            per_iter.append(round(ev0.elapsed_time(ev1), 3))
     ms /= args.iters
     nbad = hit.sum(dim=1)
     unrec = int((nbad > m).sum())
@@ -90,7 +92,7 @@ for (k, m) in ((6, 3), (10, 4)):
         if it:
             tag_ms += ev0.elapsed_time(ev1)
     tag_ms /= args.iters
-    res["rs%d_%d" % (k, m)] = {"stripes": n, "ms": round(ms, 3), "tag_pass_ms": round(tag_ms, 3),
+    res["rs%d_%d" % (k, m)] = {"stripes": n, "ms": round(ms, 3), "per_iter_ms": per_iter, "tag_pass_ms": round(tag_ms, 3),
                                "tag_pass_GBs": round(n * tot * L / tag_ms / 1e6, 1), "payload_GiBs": round(n * B / ms / 1e-3 / 2**30, 1),
                                "corrupt_shards": int(hit.sum()), "stripes_healed": int(((nbad > 0) & (nbad <= m)).sum()),
                                "unrecoverable": unrec}
