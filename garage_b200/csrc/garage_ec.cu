@@ -63,6 +63,10 @@ struct garage_ec_ctx {
     std::vector<LaneSet *> free_sets;
     int n_sets = 0;
     // NUMA placement of the GPU (from sysfs): host memory for DMA should live on this node
+    // stream-ordered scratch (decode plans of DEVICE-mode calls) comes from a pool of our own that KEEPS freed memory:
+    // the default pool hands memory back to the driver at every synchronisation, and re-mapping it on the next call
+    // cost 10-40 ms of host time at random whenever the GPU work ahead of it was short (config-5 sweep with adler8 tags)
+    cudaMemPool_t pool = nullptr;
     std::atomic<int> sum_kind{GARAGE_EC_SUM_BLAKE2};  // per-shard integrity tag (garage_ec_set_sum_kind)
     int numa_node = -1;
     bool have_node_cpus = false;
@@ -535,6 +539,21 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
         delete ctx;
         return GARAGE_EC_E_NODEVICE;
     }
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            (void)cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            ctx->pool = nullptr;  // fall back to the default pool
+        }
+        (void)cudaGetLastError();
+    }
     probe_numa(ctx);
     ctx->trace = getenv("GARAGE_EC_TRACE") != nullptr;
     *out = ctx;
@@ -607,6 +626,7 @@ void garage_ec_destroy(garage_ec_ctx *ctx)
         cudaEventDestroy(pr.second);
     }
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -983,7 +1003,8 @@ int garage_ec_reconstruct(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *pr
         return reconstruct_host(ctx, shards, nullptr, present, want, status, shard_len, stride, n_stripes);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     void *scratch = nullptr;
-    CU_TRY(ctx, cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
+    CU_TRY(ctx, ctx->pool ? cudaMallocFromPoolAsync(&scratch, plan_scratch_bytes(n_stripes), ctx->pool, st)
+                          : cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
     StripePlan *plan = reinterpret_cast<StripePlan *>(scratch);
     uint32_t *counter =
         reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scratch) + n_stripes * sizeof(StripePlan));
@@ -1038,7 +1059,7 @@ static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *ex
     // LSU-bound: measured 5.4 ms vs 7.6 ms at 18 432 shards and 6.0 vs 5.7 ms at 28 672);
     // from ~24 000 shards on one thread per shard keeps the schedulers busy enough
     if (ctx->sum_kind.load(std::memory_order_relaxed) == GARAGE_EC_SUM_ADLER8) {
-        // one block per (shard, segment), persistent grid of 8 blocks per SM
+        // one warp per (shard, segment), 8 warps per block, persistent grid
         if (n_shards >= (1u << 29)) return GARAGE_EC_E_INVALID;
         if (expect && bad) {
             // segments OR their verdict into the shard's flag: clear the flags of this launch first.  Flags of
@@ -1047,7 +1068,7 @@ static int run_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t *ex
             cudaError_t e0 = cudaMemsetAsync(bad, 0, nflags, st);
             if (e0 != cudaSuccess) return set_cuda_error(ctx, e0, "cudaMemsetAsync(bad)");
         }
-        const unsigned blocks = (unsigned)std::min<size_t>(n_shards * 8, (size_t)ctx->sm_count * 8);
+        const unsigned blocks = (unsigned)std::min<size_t>(n_shards, (size_t)ctx->sm_count * 8);
         adler8_shards_kernel<<<blocks, 256, 0, st>>>(q);
     } else if (n_shards < 24000)
         blake2sum_shards_quad_kernel<<<(unsigned)((n_shards + kQuadThreads / 4 - 1) / (kQuadThreads / 4)), kQuadThreads, 0,
@@ -1172,7 +1193,8 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
         rc = run_sums(ctx, shards, expect_sums, shard_len, stride, n_stripes * tot, (int)tot, nullptr, bad_out, st);
         if (rc) return rc;
         void *scratch = nullptr;
-        CU_TRY(ctx, cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
+        CU_TRY(ctx, ctx->pool ? cudaMallocFromPoolAsync(&scratch, plan_scratch_bytes(n_stripes), ctx->pool, st)
+                          : cudaMallocAsync(&scratch, plan_scratch_bytes(n_stripes), st));
         StripePlan *plan = reinterpret_cast<StripePlan *>(scratch);
         uint32_t *counter =
             reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scratch) + n_stripes * sizeof(StripePlan));

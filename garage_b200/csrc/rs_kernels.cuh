@@ -1646,15 +1646,16 @@ __host__ __device__ inline uint32_t adler8_seg_bytes(uint32_t len)
 
 __global__ void __launch_bounds__(256) adler8_shards_kernel(const __grid_constant__ SumParams q)
 {
-    // work unit = one SEGMENT of one shard per BLOCK: the 256 threads read one contiguous 16 B x 256 = 4 KB slab
-    // per step, up to 8 slabs in flight per thread, so a block streams a contiguous ~20 KB region (DRAM-page
-    // friendly) instead of 8 warps walking 8 different shards (ncu of the warp-per-unit versions: 50 % of DRAM
-    // peak, 4.0 TB/s).  `bad` must be zero on entry when `expect` is given (the host memsets it): segments OR their
-    // verdict into the shard's flag byte.
-    __shared__ unsigned long long s_part[3][8];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (a block-per-segment variant, 256 threads on one contiguous ~20 KB region + a shared-memory reduction, measured
+    // SLOWER: 2.2-2.9 TB/s against 4.0 TB/s, profiles/r02_summary.md)
+    // work unit = one SEGMENT of one shard per warp (8 units per shard): 8x the units of a warp-per-shard
+    // split, so the persistent grid stays balanced down to a few hundred shards (ncu of the warp-per-shard
+    // version: 50 % of DRAM peak with a 2-wave tail at 18 432 shards).  `bad` must be zero on entry when
+    // `expect` is given (the host memsets it): segments OR their verdict into the shard's flag byte.
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5;
     const uint32_t units = q.n_shards * 8u;  // host guarantees n_shards < 2^29
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+    for (uint32_t u = blockIdx.x * wpb + (threadIdx.x >> 5); u < units; u += gridDim.x * wpb) {
         const uint32_t i = u >> 3, sgi = u & 7;
         const uint8_t *p;
         uint32_t len;
@@ -1663,14 +1664,15 @@ __global__ void __launch_bounds__(256) adler8_shards_kernel(const __grid_constan
         const uint32_t seg = adler8_seg_bytes(len);
         const uint32_t start = sgi * seg;
         uint32_t tag = 1;  // Adler-32 of an empty segment
-        if (start < len) {  // block-uniform
+        if (start < len) {
             const uint32_t end = min(len, start + seg), n = end - start;
             unsigned long long A = 0, B = 0, T = 0;
-            for (uint32_t r0 = tid * 16; r0 < n; r0 += 8 * 4096) {
+            // 8 vectors per lane in flight: rel = byte offset of the vector inside the segment
+            for (uint32_t r0 = lane * 16; r0 < n; r0 += 8 * 512) {
                 uint4 v[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint32_t rel = r0 + k * 4096;
+                    const uint32_t rel = r0 + k * 512;
                     v[k] = make_uint4(0, 0, 0, 0);
                     if (rel < n) {
                         v[k] = ldg_stream(p + start + rel);  // within roundup16(len): readable
@@ -1679,7 +1681,7 @@ __global__ void __launch_bounds__(256) adler8_shards_kernel(const __grid_constan
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint32_t rel = r0 + k * 4096;
+                    const uint32_t rel = r0 + k * 512;
                     uint32_t sm = __dp4a(v[k].x, 0x01010101u, 0u);
                     sm = __dp4a(v[k].y, 0x01010101u, sm);
                     sm = __dp4a(v[k].z, 0x01010101u, sm);
@@ -1699,27 +1701,11 @@ __global__ void __launch_bounds__(256) adler8_shards_kernel(const __grid_constan
                 B += __shfl_xor_sync(0xffffffffu, B, o);
                 T += __shfl_xor_sync(0xffffffffu, T, o);
             }
-            if (lane == 0) {
-                s_part[0][warp] = A;
-                s_part[1][warp] = B;
-                s_part[2][warp] = T;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned long long a2 = 0, b2 = 0, t2 = 0;
-#pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    a2 += s_part[0][w];
-                    b2 += s_part[1][w];
-                    t2 += s_part[2][w];
-                }
-                const uint32_t a = (uint32_t)((1 + a2) % kAdlerMod);
-                const uint32_t b = (uint32_t)((n + b2 - t2) % kAdlerMod);  // B >= T: (n - rel) >= j + 1 for every byte
-                tag = (b << 16) | a;
-            }
-            __syncthreads();  // s_part is reused by the next unit
+            const uint32_t a = (uint32_t)((1 + A) % kAdlerMod);
+            const uint32_t b = (uint32_t)((n + B - T) % kAdlerMod);  // B >= T: (n - rel) >= j + 1 for every byte
+            tag = (b << 16) | a;
         }
-        if (tid == 0) {
+        if (lane == 0) {
             if (q.sums) reinterpret_cast<uint32_t *>(q.sums + oi * 32)[sgi] = tag;
             if (q.expect && q.bad && reinterpret_cast<const uint32_t *>(q.expect + oi * 32)[sgi] != tag) {
                 // set byte `oi` of bad[] to 1 through the aligned 32-bit word that contains it

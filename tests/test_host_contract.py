@@ -233,3 +233,20 @@ def test_pinned_alloc_is_numa_local_when_topology_is_known(torch):
         ec.bind_thread()
         assert len(os.sched_getaffinity(0)) >= 1
         os.sched_setaffinity(0, before)
+
+
+def test_write_combined_pinned_buffers_work_as_upload_and_download_buffers(torch):
+    """garage_ec_host_alloc_wc: upload-only / download-only landing buffers (no CPU reads on the hot path)"""
+    k, m, stride, n = 10, 4, 104960, 64
+    data, par, _ = _case(k, m, n, stride, 31337)
+    with G.GarageEc(0, k, m) as ec:
+        h_in, p1 = ec.host_alloc(n * k * stride, write_combined=True)
+        h_out, p2 = ec.host_alloc(n * m * stride, write_combined=True)
+        h_in[:] = data            # sequential CPU writes: what write-combined memory is for
+        ec.encode(h_in, h_out, stride, n)
+        assert np.array_equal(np.array(h_out), par)  # (a slow uncached read, fine in a test)
+        gpu_node, got = ec.numa_info()
+        if gpu_node >= 0 and got >= 0:
+            assert got == gpu_node
+        ec.host_free(p1)
+        ec.host_free(p2)
