@@ -120,14 +120,24 @@ struct Node {
     bool fsync_data = false;  // data_fsync (util/config.rs), manager.rs:775-789
     std::string dir;          // empty: in-memory store
     int k = 0, m = 0;
-    std::unordered_map<Hash, StoredShard, HashHasher> shards;     // in-memory mode
-    std::unordered_map<Hash, StoredShard, HashHasher> corrupted;  // the ".corrupted" quarantine
+    // in-memory mode: immutable shards behind shared pointers, so the node lock only covers the map operation -- the
+    // 100 KB copies happen outside it (the reference shards its lock 256 ways per node, manager.rs:114,679-689; with
+    // one lock per node and the copies inside it, 128 clients serialised on 14 mutexes at ~12 GiB/s)
+    using ShardPtr = std::shared_ptr<const StoredShard>;
+    std::unordered_map<Hash, ShardPtr, HashHasher> shards;
+    std::unordered_map<Hash, ShardPtr, HashHasher> corrupted;  // the ".corrupted" quarantine
     std::deque<Hash> resync_queue;                                // block_local_resync_queue (resync.rs:90)
     std::unordered_set<Hash, HashHasher> queued;
 
     std::string path_of(const Hash &h, const char *ext) const
     {
         return dir + "/" + hex_of(h.data(), 1) + "/" + hex_of(h.data() + 1, 1) + "/" + hex_of(h.data(), 32) + ext;
+    }
+    void store_put_ptr(const Hash &h, ShardPtr sp) { shards[h] = std::move(sp); }  // in-memory: the copy was made by the caller
+    ShardPtr store_find(const Hash &h) const
+    {
+        auto it = shards.find(h);
+        return it == shards.end() ? ShardPtr() : it->second;
     }
     bool meta_valid(const ShardMeta &mt) const
     {
@@ -138,9 +148,10 @@ struct Node {
     bool store_put(const Hash &h, const ShardMeta &mt, const uint8_t *bytes, size_t n)
     {
         if (dir.empty()) {
-            StoredShard &s = shards[h];
-            static_cast<ShardMeta &>(s) = mt;
-            s.bytes.assign(bytes, bytes + n);
+            auto sp = std::make_shared<StoredShard>();
+            static_cast<ShardMeta &>(*sp) = mt;
+            sp->bytes.assign(bytes, bytes + n);
+            shards[h] = std::move(sp);
             return true;
         }
         std::error_code ec;
@@ -181,10 +192,7 @@ struct Node {
         if (dir.empty()) {
             auto it = shards.find(h);
             if (it == shards.end()) return kReadMissing;
-            mt = it->second;
-            if (!meta_valid(mt) || it->second.bytes.size() != mt.shard_len || mt.shard_len > cap) return kReadInvalid;
-            if (mt.shard_len) memcpy(dst, it->second.bytes.data(), mt.shard_len);
-            return kReadOk;
+            return copy_out(*it->second, dst, cap, mt);
         }
         FILE *f = fopen(path_of(h, ".shard").c_str(), "rb");  // find_block (manager.rs:627-662)
         if (!f) return kReadMissing;
@@ -207,12 +215,19 @@ struct Node {
         fclose(f);
         return r;
     }
+    ReadResult copy_out(const StoredShard &sh, uint8_t *dst, size_t cap, ShardMeta &mt) const
+    {
+        mt = sh;
+        if (!meta_valid(mt) || sh.bytes.size() != mt.shard_len || mt.shard_len > cap) return kReadInvalid;
+        if (mt.shard_len) memcpy(dst, sh.bytes.data(), mt.shard_len);
+        return kReadOk;
+    }
     bool store_get(const Hash &h, StoredShard &out) const  // a copy (scrub snapshots, inspection)
     {
         if (dir.empty()) {
             auto it = shards.find(h);
             if (it == shards.end()) return false;
-            out = it->second;
+            out = *it->second;
             return true;
         }
         std::error_code ec;
@@ -607,7 +622,20 @@ struct garage_bm {
         memcpy(mt.sum.data(), sum32, 32);
         Node &nd = *nodes[node];
         bool ok;
-        {
+        if (nd.dir.empty()) {
+            auto sp = std::make_shared<StoredShard>();  // the copy happens before the node lock is taken
+            static_cast<ShardMeta &>(*sp) = mt;
+            sp->bytes.assign(bytes, bytes + n);
+            Node::ShardPtr old;
+            {
+                std::lock_guard<std::mutex> lk(nd.mu);
+                if (!nd.up) return false;
+                auto &slot_ref = nd.shards[h];
+                old.swap(slot_ref);
+                slot_ref = std::move(sp);
+            }
+            ok = true;  // `old` (a replaced shard) is freed here, outside the lock
+        } else {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return false;
             ok = nd.store_put(h, mt, bytes, n);
@@ -634,7 +662,15 @@ struct garage_bm {
     {
         Node &nd = *nodes[node];
         ReadResult r;
-        {
+        if (nd.dir.empty()) {
+            Node::ShardPtr sp;
+            {
+                std::lock_guard<std::mutex> lk(nd.mu);
+                if (!nd.up) return false;
+                sp = nd.store_find(h);
+            }
+            r = sp ? nd.copy_out(*sp, dst, cap, mt) : kReadMissing;  // the copy happens outside the node lock
+        } else {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return false;
             r = nd.store_read_into(h, dst, cap, mt);
@@ -1493,14 +1529,16 @@ static int bm_corrupt(garage_bm *bm, int node, const uint8_t hash[32], size_t by
     if (nd.dir.empty()) {
         auto it = nd.shards.find(h);
         if (it == nd.shards.end()) return GARAGE_BM_E_MISSING_BLOCK;
+        auto mod = std::make_shared<StoredShard>(*it->second);  // stored shards are immutable: replace by a damaged copy
         if (what == 0) {
-            if (it->second.bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
-            it->second.bytes[byte_off % it->second.bytes.size()] ^= 0x01;
+            if (mod->bytes.empty()) return GARAGE_BM_E_MISSING_BLOCK;
+            mod->bytes[byte_off % mod->bytes.size()] ^= 0x01;
         } else if (what == 1) {
-            it->second.block_len += 1;
+            mod->block_len += 1;
         } else {
-            it->second.index = (it->second.index + 1) % (bm->tot);
+            mod->index = (mod->index + 1) % (bm->tot);
         }
+        it->second = std::move(mod);
         return GARAGE_BM_OK;
     }
     FILE *f = fopen(nd.path_of(h, ".shard").c_str(), "r+b");
