@@ -75,6 +75,9 @@ struct garage_ec_ctx {
     std::atomic<long> fault_countdown{-1};
     // GARAGE_EC_TRACE=1: host-side time per phase of the block-level encode call, printed at destroy (tuning aid)
     bool trace = false;
+    // HOST-mode encode / reconstruct on pinned (device-addressable) buffers: let the kernels read and write the host
+    // memory directly over PCIe instead of staging chunks through device buffers.  GARAGE_EC_ZEROCOPY=0/1 overrides.
+    bool zero_copy = false;
     std::atomic<uint64_t> tr_calls{0}, tr_blocks{0}, tr_prep_us{0}, tr_issue_us{0}, tr_sync_us{0};    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
     std::mutex misc_mu;  // timing list, last_error
     bool timing = false;
@@ -338,7 +341,7 @@ bool make_src_tensor_map(CUtensorMap *tm, const uint8_t *src, size_t stride, siz
 // n * items_per_stripe stays below 2^32 and m > 4 runs in passes of 4 rows.
 int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pitch, uint8_t *dst,
                 size_t dst_pitch, uint32_t *mismatch, const uint32_t *shard_len, size_t stride,
-                size_t n, cudaStream_t st)
+                size_t n, cudaStream_t st, bool allow_tmap = true)
 {
     const uint32_t ips = items_per_stripe(stride);
     const size_t max_n = 0xffffffffull / ips;
@@ -362,7 +365,7 @@ int run_uniform(garage_ec_ctx *ctx, int mode, const uint8_t *src, size_t src_pit
             p.items_per_stripe = ips;
             p.row_bytes = 128;
             p.rows_per_stripe = (uint32_t)(src_pitch / stride);
-            p.use_tmap = (GEC_TMAP && ctx->k >= GEC_TMAP_FROM_K && make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe,
+            p.use_tmap = (allow_tmap && GEC_TMAP && ctx->k >= GEC_TMAP_FROM_K && make_src_tensor_map(&p.tmap, p.src, stride, cnt * p.rows_per_stripe,
                                               (GEC_SPLIT_STAGE && ctx->k > 16) ? 16 : ctx->k)) ? 1u : 0u;  // box rows: StreamCfg::kSrcRows
             for (uint32_t i = 0; i < p.rows; i++)
                 memcpy(p.coef + i * ctx->k, ctx->P + (r0 + i) * ctx->k, ctx->k);
@@ -556,6 +559,7 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
     }
     probe_numa(ctx);
     ctx->trace = getenv("GARAGE_EC_TRACE") != nullptr;
+    if (const char *z = getenv("GARAGE_EC_ZEROCOPY")) ctx->zero_copy = z[0] == '1';
     *out = ctx;
     return GARAGE_EC_OK;
 }
@@ -782,10 +786,38 @@ int garage_ec_fill_random(garage_ec_ctx *ctx, uint8_t *dst_device, size_t len, u
 }
 
 // --------------------------------------------------------------------------- ENCODE
+// pinned host memory the device addresses through the same pointer (cudaHostAlloc / cudaHostRegister under UVA)
+static bool device_addressable_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+
 static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
                        const uint32_t *shard_len, size_t stride, size_t n)
 {
     LEASE_LANES(ctx, lanes);
+    if (ctx->zero_copy && device_addressable_host(data) && device_addressable_host(parity)) {
+        // one launch over the whole batch: the TMA / vector loads pull the data shards across PCIe, the parity stores
+        // go straight to the caller's buffer -- no staging copies, no chunk boundaries
+        HostLane &L = lanes[0];
+        int rc = lane_reserve(ctx, L, 0, align_up(n * 4, 16));
+        if (rc) return rc;
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small, shard_len, n * 4, cudaMemcpyHostToDevice, L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small);
+        }
+        rc = run_uniform(ctx, kModeEncode, data, ctx->k * stride, parity, ctx->m * stride, nullptr, d_len, stride, n, L.stream,
+                         /*allow_tmap=*/false);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        return GARAGE_EC_OK;
+    }
     const size_t k = ctx->k, m = ctx->m;
     size_t cs = kHostChunkBytes / (k * stride);
     if (cs < 1) cs = 1;
@@ -905,6 +937,37 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, uint8_t *const 
     std::vector<int32_t> st_host(status ? 0 : n);
     CopyBatch up, down;
     LEASE_LANES(ctx, lanes);
+    if (ctx->zero_copy && !stripes && device_addressable_host(shards)) {
+        // the kernel reads the k survivors of every stripe and writes the rebuilt shards in the caller's pinned buffer
+        const size_t tot_ = ctx->k + ctx->m;
+        const size_t zo_present = 0, zo_want = align_up(n * tot_, 16), zo_status = zo_want + align_up(n * tot_, 16);
+        const size_t zo_len = zo_status + align_up(n * 4, 16), zo_plan = zo_len + align_up(n * 4, 16);
+        HostLane &L = lanes[0];
+        int rcz = lane_reserve(ctx, L, 0, zo_plan + plan_scratch_bytes(n));
+        if (rcz) return rcz;
+        CU_TRY(ctx, cudaMemcpyAsync(L.d_small + zo_present, present, n * tot_, cudaMemcpyHostToDevice, L.stream));
+        const uint8_t *d_want = nullptr;
+        if (want) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + zo_want, want, n * tot_, cudaMemcpyHostToDevice, L.stream));
+            d_want = L.d_small + zo_want;
+        }
+        const uint32_t *d_len = nullptr;
+        if (shard_len) {
+            CU_TRY(ctx, cudaMemcpyAsync(L.d_small + zo_len, shard_len, n * 4, cudaMemcpyHostToDevice, L.stream));
+            d_len = reinterpret_cast<const uint32_t *>(L.d_small + zo_len);
+        }
+        StripePlan *d_plan = reinterpret_cast<StripePlan *>(L.d_small + zo_plan);
+        uint32_t *d_counter = reinterpret_cast<uint32_t *>(L.d_small + zo_plan + n * sizeof(StripePlan));
+        rcz = run_reconstruct(ctx, shards, L.d_small + zo_present, d_want, reinterpret_cast<int32_t *>(L.d_small + zo_status), d_len,
+                              stride, n, d_plan, d_counter, L.stream);
+        if (rcz) return rcz;
+        int32_t *st_o = status ? status : st_host.data();
+        CU_TRY(ctx, cudaMemcpyAsync(st_o, L.d_small + zo_status, n * 4, cudaMemcpyDeviceToHost, L.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        for (size_t s = 0; s < n; s++)
+            if (st_o[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
+        return GARAGE_EC_OK;
+    }
     const size_t k = ctx->k, tot = ctx->k + ctx->m;
     size_t cs = kHostChunkBytes / (tot * stride);
     if (cs < 1) cs = 1;
