@@ -777,7 +777,9 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
         "h2d_bytes_per_step": int(world * (up_enc + up_dec)),
         "d2h_bytes_per_step": int(world * (dn_enc + dn_dec)),
         "api": "garage_ec_encode + garage_ec_reconstruct, GARAGE_EC_MEM_HOST, pinned buffers from garage_ec_host_alloc "
-               "(NUMA-local to the GPU), calling thread bound to the GPU's node (garage_ec_bind_thread)",
+               "(NUMA-local to the GPU), calling thread bound to the GPU's node (garage_ec_bind_thread); encode stages 48 MB "
+               "chunks through three lanes, reconstruct reads the survivors and writes the rebuilt shards in the pinned host "
+               "buffer directly from the kernel (both inside the timed region, both over PCIe)",
         "timer": "host wall clock around synchronous calls (max over ranks)", "checked": bool(ok),
         # per-rank link numbers: which rank (which socket / root complex) limits the job
         "per_rank": [{"rank": i, "GiBs": 2 * int(r[6]) * B * steps / r[0] / GIB,

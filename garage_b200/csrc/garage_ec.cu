@@ -75,9 +75,12 @@ struct garage_ec_ctx {
     std::atomic<long> fault_countdown{-1};
     // GARAGE_EC_TRACE=1: host-side time per phase of the block-level encode call, printed at destroy (tuning aid)
     bool trace = false;
-    // HOST-mode encode / reconstruct on pinned (device-addressable) buffers: let the kernels read and write the host
-    // memory directly over PCIe instead of staging chunks through device buffers.  GARAGE_EC_ZEROCOPY=0/1 overrides.
-    bool zero_copy = false;
+    // HOST-mode calls on pinned (device-addressable) buffers: let the kernel read and write the host memory directly
+    // over PCIe instead of staging chunks through device buffers.  Measured on one B200 (profiles/r02_summary.md):
+    // reconstruct, whose staged form moves ~130 scattered 100 KB pieces per chunk in each direction, goes from
+    // 39.7 + 15.9 GB/s (up + down) to 49.9 + 20.0 GB/s; encode, one contiguous copy per chunk, is faster staged
+    // (53.3 vs 49.9 GB/s).  Default: reconstruct only.  GARAGE_EC_ZEROCOPY=0 turns it off, =1 also applies it to encode.
+    bool zero_copy_rec = true, zero_copy_enc = false;
     std::atomic<uint64_t> tr_calls{0}, tr_blocks{0}, tr_prep_us{0}, tr_issue_us{0}, tr_sync_us{0};    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
     std::mutex misc_mu;  // timing list, last_error
     bool timing = false;
@@ -559,7 +562,7 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
     }
     probe_numa(ctx);
     ctx->trace = getenv("GARAGE_EC_TRACE") != nullptr;
-    if (const char *z = getenv("GARAGE_EC_ZEROCOPY")) ctx->zero_copy = z[0] == '1';
+    if (const char *z = getenv("GARAGE_EC_ZEROCOPY")) ctx->zero_copy_rec = ctx->zero_copy_enc = z[0] == '1';
     *out = ctx;
     return GARAGE_EC_OK;
 }
@@ -801,7 +804,7 @@ static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
                        const uint32_t *shard_len, size_t stride, size_t n)
 {
     LEASE_LANES(ctx, lanes);
-    if (ctx->zero_copy && device_addressable_host(data) && device_addressable_host(parity)) {
+    if (ctx->zero_copy_enc && device_addressable_host(data) && device_addressable_host(parity)) {
         // one launch over the whole batch: the TMA / vector loads pull the data shards across PCIe, the parity stores
         // go straight to the caller's buffer -- no staging copies, no chunk boundaries
         HostLane &L = lanes[0];
@@ -937,7 +940,7 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, uint8_t *const 
     std::vector<int32_t> st_host(status ? 0 : n);
     CopyBatch up, down;
     LEASE_LANES(ctx, lanes);
-    if (ctx->zero_copy && !stripes && device_addressable_host(shards)) {
+    if (ctx->zero_copy_rec && !stripes && device_addressable_host(shards)) {
         // the kernel reads the k survivors of every stripe and writes the rebuilt shards in the caller's pinned buffer
         const size_t tot_ = ctx->k + ctx->m;
         const size_t zo_present = 0, zo_want = align_up(n * tot_, 16), zo_status = zo_want + align_up(n * tot_, 16);

@@ -250,3 +250,45 @@ def test_write_combined_pinned_buffers_work_as_upload_and_download_buffers(torch
             assert got == gpu_node
         ec.host_free(p1)
         ec.host_free(p2)
+
+
+def test_reconstruct_on_pinned_buffers_runs_in_place_over_pcie(torch):
+    """HOST reconstruct on pinned (device-addressable) buffers takes the zero-copy path: the kernel reads the
+    survivors from, and writes the rebuilt shards into, the caller's buffer.  Same results as the staged path,
+    absent shards may hold garbage, present shards are never written, want masks and unrecoverable stripes work."""
+    k, m, stride, n = 10, 4, 104960, 96
+    tot = k + m
+    _, _, sh = _case(k, m, n, stride, 2718)
+    lens = np.full(n, 104858, dtype=np.uint32)
+    rng = np.random.default_rng(5)
+    present = np.ones((n, tot), dtype=np.uint8)
+    for s in range(n):
+        present[s, rng.choice(tot, int(rng.integers(0, m + 1)), replace=False)] = 0
+    present[7, : m + 1] = 0  # unrecoverable
+    want = np.ones((n, tot), dtype=np.uint8)
+    want[:, k:] = 0  # GET: data shards only
+    with G.GarageEc(0, k, m) as ec:
+        buf, p = ec.host_alloc(n * tot * stride)
+        v = buf.reshape(n, tot, stride)
+        v[:] = sh
+        v[present == 0] = 0x77
+        st = np.zeros(n, dtype=np.int32)
+        rc = ec.reconstruct(buf, present, stride, n, want=want, status=st, shard_len=lens)
+        assert rc == G.E_UNRECOVERABLE and st[7] == G.E_UNRECOVERABLE and np.count_nonzero(st) == 1
+        for s in range(n):
+            for i in range(tot):
+                got = v[s, i, :104858]
+                if present[s, i] or s == 7:
+                    expect = sh[s, i, :104858] if present[s, i] else np.full(104858, 0x77, dtype=np.uint8)
+                elif i < k:
+                    expect = sh[s, i, :104858]            # rebuilt
+                else:
+                    expect = np.full(104858, 0x77, dtype=np.uint8)  # absent parity, not wanted: untouched
+                assert np.array_equal(got, expect), (s, i)
+        # and it is the same answer the staged path gives on pageable memory
+        pg = sh.copy()
+        pg[present == 0] = 0x77
+        st2 = np.zeros(n, dtype=np.int32)
+        ec.reconstruct(pg.reshape(-1), present, stride, n, want=want, status=st2, shard_len=lens)
+        assert np.array_equal(st, st2) and np.array_equal(pg[:, :, :104858], v[:, :, :104858])
+        ec.host_free(p)
