@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "garage_ec_shard_sums", "garage_ec_check_sums", "garage_ec_blake2sum",
     "garage_ec_encode_blocks_with_sums", "garage_ec_scrub_repair",
     "garage_ec_numa_info", "garage_ec_bind_thread", "garage_ec_debug_fail_after",
-    "garage_ec_set_sum_kind", "garage_ec_shard_sum_host", "garage_ec_reconstruct_stripes",
+    "garage_ec_set_sum_kind", "garage_ec_set_wait_mode", "garage_ec_copy_for_dma", "garage_ec_shard_sum_host", "garage_ec_reconstruct_stripes",
 ]
 
 
@@ -108,6 +108,9 @@ def load_library(build=True):
     L.garage_ec_debug_fail_after.argtypes = [vp, C.c_long]
     L.garage_ec_reconstruct_stripes.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz]
     L.garage_ec_set_sum_kind.argtypes = [vp, i32]
+    L.garage_ec_set_wait_mode.argtypes = [vp, i32]
+    L.garage_ec_copy_for_dma.argtypes = [vp, vp, C.c_size_t]
+    L.garage_ec_copy_for_dma.restype = None
     L.garage_ec_shard_sum_host.argtypes = [i32, vp, sz, vp]
     _lib = L
     return L
@@ -134,6 +137,12 @@ def shard_sum_host(kind, data) -> bytes:
     if rc:
         raise EcError(rc, "shard_sum_host")
     return out.tobytes()
+
+
+def copy_for_dma(dst, src):
+    """copy `src` into `dst` (numpy uint8 views, dst normally pinned) with non-temporal stores: garage_ec_copy_for_dma"""
+    assert dst.dtype == np.uint8 and src.dtype == np.uint8 and dst.size >= src.size
+    load_library().garage_ec_copy_for_dma(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), src.size)
 
 
 def _ptr(x):
@@ -321,6 +330,10 @@ class GarageEc:
     def bind_thread(self):
         """pin the calling thread to the CPUs of the GPU's NUMA node; True if bound"""
         return self._L.garage_ec_bind_thread(self._h) == 0
+
+    def set_wait_mode(self, blocking):
+        """HOST-mode calls wait by sleeping on an event (True) instead of spinning in the driver (False, default)"""
+        self._check(self._L.garage_ec_set_wait_mode(self._h, 1 if blocking else 0))
 
     def set_sum_kind(self, kind):
         self._check(self._L.garage_ec_set_sum_kind(self._h, kind))

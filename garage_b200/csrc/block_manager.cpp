@@ -61,6 +61,9 @@ Hash to_hash(const uint8_t *p)
     return h;
 }
 
+// copy into a pinned buffer the GPU reads next (landing copy of a PUT, survivors of a degraded GET)
+inline void copy_for_dma(uint8_t *dst, const uint8_t *src, size_t n) { garage_ec_copy_for_dma(dst, src, n); }
+
 uint32_t adler32_small(const uint8_t *p, size_t n)
 {
     uint32_t a = 1, b = 0;
@@ -357,11 +360,12 @@ struct Node {
         fclose(f);
         return r;
     }
-    ReadResult copy_out(const StoredShard &sh, uint8_t *dst, size_t cap, ShardMeta &mt) const
+    ReadResult copy_out(const StoredShard &sh, uint8_t *dst, size_t cap, ShardMeta &mt, bool for_dma = false) const
     {
         mt = sh;
         if (!meta_valid(mt) || sh.bytes.size() != mt.shard_len || mt.shard_len > cap) return kReadInvalid;
-        if (mt.shard_len) memcpy(dst, sh.bytes.data(), mt.shard_len);
+        if (for_dma) copy_for_dma(dst, sh.bytes.data(), mt.shard_len);
+        else if (mt.shard_len) memcpy(dst, sh.bytes.data(), mt.shard_len);
         return kReadOk;
     }
     bool store_get(const Hash &h, StoredShard &out) const  // a copy (scrub snapshots, inspection)
@@ -803,18 +807,21 @@ struct garage_bm {
 
     // manager.rs:554-609 read_block + read_block_from: the verified shard bytes land in `dst`.
     // A bad header or a tag mismatch quarantines the shard and queues a resync, like the reference.
-    bool read_shard_into(int node, const Hash &h, uint8_t *dst, size_t cap, ShardMeta &mt)
+    // `for_dma`: the GPU reads `dst` next (degraded GET, resync): see copy_for_dma
+    bool read_shard_into(int node, const Hash &h, uint8_t *dst, size_t cap, ShardMeta &mt, bool for_dma = false)
     {
         Node &nd = *nodes[node];
         ReadResult r;
+        const uint8_t *check = dst;
+        Node::ShardPtr sp;
         if (nd.dir.empty()) {
-            Node::ShardPtr sp;
             {
                 std::lock_guard<std::mutex> lk(nd.mu);
                 if (!nd.up) return false;
                 sp = nd.store_find(h);
             }
-            r = sp ? nd.copy_out(*sp, dst, cap, mt) : kReadMissing;  // the copy happens outside the node lock
+            r = sp ? nd.copy_out(*sp, dst, cap, mt, for_dma) : kReadMissing;  // the copy happens outside the node lock
+            if (sp && for_dma) check = sp->bytes.data();  // same bytes, and these are still in the cache
         } else {
             std::lock_guard<std::mutex> lk(nd.mu);
             if (!nd.up) return false;
@@ -824,7 +831,7 @@ struct garage_bm {
         if (r == kReadOk) {
             bytes_read += mt.shard_len;
             Hash got;
-            if (garage_ec_shard_sum_host(mt.sum_kind, dst, mt.shard_len, got.data()) == GARAGE_EC_OK && got == mt.sum)
+            if (garage_ec_shard_sum_host(mt.sum_kind, check, mt.shard_len, got.data()) == GARAGE_EC_OK && got == mt.sum)
                 return true;
         }
         quarantine(node, h);
@@ -897,7 +904,8 @@ struct garage_bm {
     // copy (manager.rs:292-334); RpcHelper::try_call_many with quorum k is the real-cluster form.
     // A shard whose header disagrees with the others on the block length, or that sits under the
     // wrong index, is treated like a corrupt one.  `all`: do not stop at k (corruption hunting).
-    int gather_into(const Hash &h, int skip_node, uint8_t *slot, uint8_t *have, uint32_t &block_len, bool all = false)
+    int gather_into(const Hash &h, int skip_node, uint8_t *slot, uint8_t *have, uint32_t &block_len, bool all = false,
+                    bool for_gpu = false)
     {
         int who[64];
         storage_nodes_of(h, who);
@@ -916,7 +924,7 @@ struct garage_bm {
         auto try_shard = [&](int i) {
             if (who[i] == skip_node || have[i]) return;
             ShardMeta mt;
-            if (!read_shard_into(who[i], h, slot + (size_t)i * slot_stride, slot_stride, mt)) return;
+            if (!read_shard_into(who[i], h, slot + (size_t)i * slot_stride, slot_stride, mt, for_gpu)) return;
             if (mt.index != i || (have_expect && mt.block_len != expect)) {
                 quarantine(who[i], h);  // a stale or misplaced shard with a self-consistent tag
                 return;
@@ -928,7 +936,10 @@ struct garage_bm {
             have[i] = 1;
             count++;
         };
-        for (int i = 0; i < k; i++) try_shard(i);
+        for (int i = 0; i < k; i++) {
+            try_shard(i);
+            for_gpu |= !have[i];  // a data shard is missing: this stripe goes through the GPU
+        }
         for (int i = k; i < tot && (all || count < k); i++) try_shard(i);
         block_len = expect;
         return count;
@@ -982,7 +993,7 @@ struct garage_bm {
         const auto t_in = Clock::now();
         SlotLease slot(put_slots);
         const auto t_slot = Clock::now();
-        memcpy(slot.p, data, len);
+        copy_for_dma(slot.p, data, len);  // landing copy: the GPU reads the slot next
         EncodeItem it;
         it.data = slot.p;
         it.len = (uint32_t)len;
@@ -1062,7 +1073,7 @@ struct garage_bm {
         // stale or was rebuilt wrongly.  Find it: gather everything, drop one shard at a time,
         // rebuild, re-check (manager.rs read path: CorruptData -> quarantine + resync).
         corrupt_data_errors++;
-        const int avail = gather_into(h, -1, slot.p, have, block_len, /*all=*/true);
+        const int avail = gather_into(h, -1, slot.p, have, block_len, /*all=*/true, /*for_gpu=*/true);
         if (avail > k && block_len <= cap) {
             int who[64];
             storage_nodes_of(h, who);
@@ -1131,7 +1142,7 @@ struct garage_bm {
         SlotLease slot(stripe_slots);
         uint8_t have[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M], want[GARAGE_EC_MAX_K + GARAGE_EC_MAX_M] = {0};
         uint32_t block_len = 0;
-        const int count = gather_into(h, node, slot.p, have, block_len);
+        const int count = gather_into(h, node, slot.p, have, block_len, false, /*for_gpu=*/true);
         if (count < k) {
             resync_error_counter++;
             return GARAGE_BM_E_MISSING_BLOCK;  // resync.rs:488-494
@@ -1526,6 +1537,10 @@ static int bm_create(garage_bm **out, const garage_bm_config *cfg)
         if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
         garage_ec_set_sum_kind(bm->enc_ctx[w], bm->sum_kind);
         garage_ec_set_sum_kind(bm->rec_ctx[w], bm->sum_kind);
+        // the dispatchers sleep while their batch is on the GPU: the CPUs belong to the callers' copies
+        const int sleep_wait = getenv("GARAGE_BM_SPIN_WAIT") ? 0 : 1;  // (=1: spin, for A/B measurements)
+        garage_ec_set_wait_mode(bm->enc_ctx[w], sleep_wait);
+        garage_ec_set_wait_mode(bm->rec_ctx[w], sleep_wait);
         for (auto &eb : bm->enc_out[w]) eb.ctx = bm->enc_ctx[w];
         // the pinned parity buffers at their final size now, not on the first large batch
         const size_t out_bytes = (size_t)std::max<uint32_t>(cfg->batch_max_blocks, 1) * ((size_t)m * bm->slot_stride + (size_t)(k + m) * 32);

@@ -5,6 +5,9 @@
 // Result<_, Error> convention (src/util/error.rs:14-82).
 #include "../../include/garage_ec.h"
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <cuda_runtime.h>
 
 #include <sched.h>
@@ -43,6 +46,7 @@ struct HostLane {
     size_t d_cap = 0;
     uint8_t *d_small = nullptr;  // shard_len / present / want / status / mismatch / plan
     size_t small_cap = 0;
+    cudaEvent_t done = nullptr;  // blocking-sync event (garage_ec_set_wait_mode)
 };
 // One HOST-mode call owns one set of lanes for its duration; concurrent callers (tokio
 // spawn_blocking threads, src/block/block.rs:86) get different sets, up to kMaxLaneSets.
@@ -75,13 +79,18 @@ struct garage_ec_ctx {
     std::atomic<long> fault_countdown{-1};
     // GARAGE_EC_TRACE=1: host-side time per phase of the block-level encode call, printed at destroy (tuning aid)
     bool trace = false;
+    // how a HOST-mode call waits for its lanes: 0 = cudaStreamSynchronize (the driver spins: lowest latency, one CPU
+    // per waiting caller), 1 = block on an event (garage_ec_set_wait_mode)
+    std::atomic<int> wait_blocking{0};
     // HOST-mode calls on pinned (device-addressable) buffers: let the kernel read and write the host memory directly
     // over PCIe instead of staging chunks through device buffers.  Measured on one B200 (profiles/r02_summary.md):
     // reconstruct, whose staged form moves ~130 scattered 100 KB pieces per chunk in each direction, goes from
     // 39.7 + 15.9 GB/s (up + down) to 49.9 + 20.0 GB/s; encode, one contiguous copy per chunk, is faster staged
     // (53.3 vs 49.9 GB/s).  Default: reconstruct only.  GARAGE_EC_ZEROCOPY=0 turns it off, =1 also applies it to encode.
     bool zero_copy_rec = true, zero_copy_enc = false;
-    std::atomic<uint64_t> tr_calls{0}, tr_blocks{0}, tr_prep_us{0}, tr_issue_us{0}, tr_sync_us{0};    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
+    std::atomic<uint64_t> tr_calls{0}, tr_blocks{0}, tr_prep_us{0}, tr_issue_us{0}, tr_sync_us{0};
+    std::atomic<uint64_t> tr_gpu_ns[4] = {};  // device time of the first chunk: H2D | split+encode | parity D2H | tags + D2H
+    // test hook: fail the n-th staged operation (see garage_ec_debug_fail_after)
     std::mutex misc_mu;  // timing list, last_error
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -116,6 +125,17 @@ inline bool fault_hit(garage_ec_ctx *ctx)
         cudaError_t e__ = (expr);                                                                  \
         if (e__ != cudaSuccess) return set_cuda_error(ctx, e__, #expr);                            \
     } while (0)
+
+// wait for everything queued on a lane (see garage_ec_ctx::wait_blocking)
+inline cudaError_t lane_wait(garage_ec_ctx *ctx, HostLane &L)
+{
+    if (!ctx->wait_blocking.load(std::memory_order_relaxed)) return cudaStreamSynchronize(L.stream);
+    cudaError_t e = cudaSuccess;
+    if (!L.done) e = cudaEventCreateWithFlags(&L.done, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(L.done, L.stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(L.done);
+    return e;
+}
 
 // Lease of one lane set for the duration of a HOST-mode call.  The destructor waits for every
 // lane stream BEFORE the set goes back to the pool -- and therefore before the entry point
@@ -562,6 +582,7 @@ int create_common(garage_ec_ctx **out, int device, int k, int m, const uint8_t *
     }
     probe_numa(ctx);
     ctx->trace = getenv("GARAGE_EC_TRACE") != nullptr;
+    if (const char *b = getenv("GARAGE_EC_BATCHCOPY")) ctx->batch_copy_ok.store(b[0] != '0');
     if (const char *z = getenv("GARAGE_EC_ZEROCOPY")) ctx->zero_copy_rec = ctx->zero_copy_enc = z[0] == '1';
     *out = ctx;
     return GARAGE_EC_OK;
@@ -616,6 +637,10 @@ void garage_ec_destroy(garage_ec_ctx *ctx)
                 (void *)ctx, (unsigned long long)ctx->tr_calls.load(), (unsigned long long)ctx->tr_blocks.load(),
                 (double)ctx->tr_prep_us.load() / ctx->tr_calls.load(), (double)ctx->tr_issue_us.load() / ctx->tr_calls.load(),
                 (double)ctx->tr_sync_us.load() / ctx->tr_calls.load());
+    if (ctx->trace && ctx->tr_calls.load())
+        fprintf(stderr, "    device time of the first chunk per call: H2D %.1f us, split+encode %.1f us, parity D2H %.1f us, tags+D2H %.1f us\n",
+                ctx->tr_gpu_ns[0].load() / 1e3 / ctx->tr_calls.load(), ctx->tr_gpu_ns[1].load() / 1e3 / ctx->tr_calls.load(),
+                ctx->tr_gpu_ns[2].load() / 1e3 / ctx->tr_calls.load(), ctx->tr_gpu_ns[3].load() / 1e3 / ctx->tr_calls.load());
     cudaSetDevice(ctx->device);
     for (LaneSet *set : ctx->free_sets) {
         for (HostLane &L : set->lanes) {
@@ -625,6 +650,7 @@ void garage_ec_destroy(garage_ec_ctx *ctx)
             }
             if (L.d_buf) cudaFree(L.d_buf);
             if (L.d_small) cudaFree(L.d_small);
+            if (L.done) cudaEventDestroy(L.done);
         }
         delete set;
     }
@@ -818,7 +844,7 @@ static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
         rc = run_uniform(ctx, kModeEncode, data, ctx->k * stride, parity, ctx->m * stride, nullptr, d_len, stride, n, L.stream,
                          /*allow_tmap=*/false);
         if (rc) return rc;
-        CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        CU_TRY(ctx, lane_wait(ctx, L));
         return GARAGE_EC_OK;
     }
     const size_t k = ctx->k, m = ctx->m;
@@ -848,7 +874,7 @@ static int encode_host(garage_ec_ctx *ctx, const uint8_t *data, uint8_t *parity,
         CU_TRY(ctx, cudaMemcpyAsync(parity + s0 * m * stride, L.d_buf + in_b, cnt * m * stride,
                                     cudaMemcpyDeviceToHost, L.stream));
     }
-    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
     return GARAGE_EC_OK;
 }
 
@@ -902,7 +928,7 @@ static int verify_host(garage_ec_ctx *ctx, const uint8_t *shards, uint32_t *mism
         if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(mismatch + s0, d_mm, cnt * 4, cudaMemcpyDeviceToHost, L.stream));
     }
-    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
     return GARAGE_EC_OK;
 }
 
@@ -966,7 +992,7 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, uint8_t *const 
         if (rcz) return rcz;
         int32_t *st_o = status ? status : st_host.data();
         CU_TRY(ctx, cudaMemcpyAsync(st_o, L.d_small + zo_status, n * 4, cudaMemcpyDeviceToHost, L.stream));
-        CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        CU_TRY(ctx, lane_wait(ctx, L));
         for (size_t s = 0; s < n; s++)
             if (st_o[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
         return GARAGE_EC_OK;
@@ -1047,7 +1073,7 @@ static int reconstruct_host(garage_ec_ctx *ctx, uint8_t *shards, uint8_t *const 
         rc = down.flush(ctx, cudaMemcpyDeviceToHost, L.stream);
         if (rc) return rc;
     }
-    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
     for (size_t s = 0; s < n; s++)
         if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
     return GARAGE_EC_OK;
@@ -1201,7 +1227,7 @@ static int sums_common(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_t 
             CU_TRY(ctx, cudaMemcpyAsync(bad_out + s0 * per, L.d_small + o_bad, cnt * per, cudaMemcpyDeviceToHost,
                                         L.stream));
     }
-    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
     return GARAGE_EC_OK;
 }
 
@@ -1223,6 +1249,49 @@ int garage_ec_check_sums(garage_ec_ctx *ctx, const uint8_t *shards, const uint8_
 }
 
 void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]) { blake2sum_host(data, len, out32); }
+
+// A plain memcpy leaves the destination lines modified in the writing core's cache, and the DMA read that follows has
+// to pull them out of there snoop by snoop: measured on the B200 hosts, 6.7 GB/s for the upload of a batch of freshly
+// landed 1 MiB blocks against 45 GB/s for the same batch at rest in DRAM (profiles/r02_summary.md).  Non-temporal
+// stores send the lines to memory instead.  GARAGE_EC_NT_COPY=0 falls back to memcpy (A/B measurements).
+void garage_ec_copy_for_dma(void *dst_v, const void *src_v, size_t n)
+{
+    uint8_t *dst = static_cast<uint8_t *>(dst_v);
+    const uint8_t *src = static_cast<const uint8_t *>(src_v);
+#if defined(__x86_64__)
+    static const bool nt = [] {
+        const char *e = getenv("GARAGE_EC_NT_COPY");
+        return !(e && e[0] == '0');
+    }();
+    if (nt && n >= 4096) {
+        const size_t head = (size_t)(-(uintptr_t)dst & 63);
+        memcpy(dst, src, head);
+        dst += head, src += head, n -= head;
+        const size_t body = n & ~(size_t)63;
+        for (size_t i = 0; i < body; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+        }
+        _mm_sfence();
+        memcpy(dst + body, src + body, n - body);
+        return;
+    }
+#endif
+    if (n) memcpy(dst, src, n);
+}
+
+int garage_ec_set_wait_mode(garage_ec_ctx *ctx, int blocking)
+{
+    if (!ctx || (blocking != 0 && blocking != 1)) return GARAGE_EC_E_INVALID;
+    ctx->wait_blocking.store(blocking, std::memory_order_relaxed);
+    return GARAGE_EC_OK;
+}
 
 int garage_ec_set_sum_kind(garage_ec_ctx *ctx, int kind)
 {
@@ -1296,7 +1365,7 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
         Pending &P = pend[lane_i];
         if (!P.active) return GARAGE_EC_OK;
         HostLane &L = lanes[lane_i];
-        CU_TRY(ctx, cudaStreamSynchronize(L.stream));  // bad flags + status of this chunk are on the host
+        CU_TRY(ctx, lane_wait(ctx, L));  // bad flags + status of this chunk are on the host
         for (size_t s = P.s0; s < P.s0 + P.cnt; s++) {
             if (st_out[s] != 0) continue;
             const size_t len = shard_len ? shard_len[s] : stride;
@@ -1343,7 +1412,7 @@ int garage_ec_scrub_repair(garage_ec_ctx *ctx, uint8_t *shards, const uint8_t *e
         rc = finish(l);
         if (rc) return rc;
     }
-    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
     for (size_t s = 0; s < n_stripes; s++)
         if (st_out[s] != 0) return GARAGE_EC_E_UNRECOVERABLE;
     return GARAGE_EC_OK;
@@ -1388,13 +1457,20 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
     }
     const size_t o_blen = cs * 4, o_sums = align_up(cs * 8, 16);
     const auto tr1 = std::chrono::steady_clock::now();
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (ctx->trace)
+        for (auto &e : tev) cudaEventCreate(&e);
+    auto mark = [&](int i, size_t chunk, cudaStream_t st) {
+        if (ctx->trace && chunk == 0 && tev[i]) cudaEventRecord(tev[i], st);
+    };
     size_t c = 0;
     for (size_t s0 = 0; s0 < n_blocks; s0 += cs, c++) {
         const size_t lane_i = c % kHostLanes;
         HostLane &L = lanes[lane_i];
         const size_t cnt = n_blocks - s0 < cs ? n_blocks - s0 : cs;
         // the pageable `lens` slot of this lane is reused: wait for the lane's previous chunk
-        if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        if (c >= (size_t)kHostLanes) CU_TRY(ctx, lane_wait(ctx, L));
+        mark(0, c, L.stream);
         uint32_t *hl = lens.data() + lane_i * 2 * cs, *hb = hl + cs;
         uint8_t *d_blk = L.d_buf, *d_data = L.d_buf + blk_b, *d_par = d_data + in_b;
         for (size_t s = 0; s < cnt; s++) {
@@ -1407,6 +1483,7 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         if (rc) return rc;
         CU_TRY(ctx, cudaMemcpyAsync(L.d_small, hl, cnt * 4, cudaMemcpyHostToDevice, L.stream));
         CU_TRY(ctx, cudaMemcpyAsync(L.d_small + o_blen, hb, cnt * 4, cudaMemcpyHostToDevice, L.stream));
+        mark(1, c, L.stream);
         SplitParams sp;
         sp.blocks = d_blk;
         sp.block_len = reinterpret_cast<const uint32_t *>(L.d_small + o_blen);
@@ -1415,13 +1492,17 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         sp.stride = (uint32_t)stride;
         sp.k = (uint32_t)k;
         sp.n = (uint32_t)cnt;
-        split_blocks_kernel<<<(unsigned)std::min<size_t>(cnt, (size_t)ctx->sm_count * 8), 256, 0, L.stream>>>(sp);
+        // ~4 CTAs per SM whatever the batch size (one CTA per block left 13 SMs copying 1 MiB each: 150 us)
+        sp.parts = (uint32_t)std::max<size_t>(1, std::min<size_t>(64, ((size_t)ctx->sm_count * 4 + cnt - 1) / cnt));
+        split_blocks_kernel<<<(unsigned)std::min<size_t>(cnt * sp.parts, (size_t)ctx->sm_count * 8), 256, 0, L.stream>>>(sp);
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         CU_TRY(ctx, cudaGetLastError());
         rc = run_uniform(ctx, kModeEncode, d_data, k * stride, d_par, m * stride, nullptr,
                          reinterpret_cast<const uint32_t *>(L.d_small), stride, cnt, L.stream);
         if (rc) return rc;
+        mark(2, c, L.stream);
         CU_TRY(ctx, cudaMemcpyAsync(parity_out + s0 * m * stride, d_par, cnt * m * stride, cudaMemcpyDeviceToHost, L.stream));
+        mark(3, c, L.stream);
         if (sums_out) {
             // per-shard tags of all k+m shards while they are on the device (row f2): [s][k+m][32]
             const uint32_t *d_len = reinterpret_cast<const uint32_t *>(L.d_small);
@@ -1431,9 +1512,10 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
             CU_TRY(ctx, cudaMemcpyAsync(sums_out + s0 * (k + m) * 32, L.d_small + o_sums, cnt * (k + m) * 32,
                                         cudaMemcpyDeviceToHost, L.stream));
         }
+        mark(4, c, L.stream);
     }
     const auto tr2 = std::chrono::steady_clock::now();
-    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+    for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
     if (ctx->trace) {
         const auto tr3 = std::chrono::steady_clock::now();
         auto us = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
@@ -1442,6 +1524,14 @@ int garage_ec_encode_blocks_with_sums(garage_ec_ctx *ctx, const uint8_t *const *
         ctx->tr_prep_us += us(tr0, tr1);
         ctx->tr_issue_us += us(tr1, tr2);
         ctx->tr_sync_us += us(tr2, tr3);
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            if (tev[i] && tev[i + 1] && cudaEventElapsedTime(&ms, tev[i], tev[i + 1]) == cudaSuccess)
+                ctx->tr_gpu_ns[i] += (uint64_t)(ms * 1e6);
+        }
+        (void)cudaGetLastError();
+        for (auto e : tev)
+            if (e) cudaEventDestroy(e);  // (an error return above leaks them: trace mode is a tuning aid only)
     }
     return GARAGE_EC_OK;
 }
@@ -1497,7 +1587,7 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
             const size_t lane_i = c % kHostLanes;
             HostLane &L = lanes[lane_i];
             const size_t cnt = need.size() - q0 < cs ? need.size() - q0 : cs;
-            if (c >= (size_t)kHostLanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+            if (c >= (size_t)kHostLanes) CU_TRY(ctx, lane_wait(ctx, L));
             uint8_t *hp = h_small.data() + lane_i * (2 * cs * tot + cs * 4);
             uint8_t *hw = hp + cs * tot;
             uint32_t *hl = reinterpret_cast<uint32_t *>(hw + cs * tot);
@@ -1558,7 +1648,7 @@ int garage_ec_decode_blocks(garage_ec_ctx *ctx, const uint8_t *shards, const uin
                 memcpy(blocks_out[s] + off, shards + (s * tot + j) * stride, have);
             }
         }
-        for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, cudaStreamSynchronize(L.stream));
+        for (HostLane &L : lanes.set->lanes) CU_TRY(ctx, lane_wait(ctx, L));
         return any_bad ? GARAGE_EC_E_UNRECOVERABLE : GARAGE_EC_OK;
     }
     for (size_t s = 0; s < n_blocks; s++) {

@@ -1598,15 +1598,20 @@ struct SplitParams {
     uint8_t *shards;             // shard j of block s at shards + (s*k + j)*stride
     unsigned long long block_pitch;
     uint32_t stride, k, n;
+    uint32_t parts;              // CTAs per block: a dispatcher batch of a dozen blocks still has to fill 148 SMs
 };
 __global__ void __launch_bounds__(256) split_blocks_kernel(const __grid_constant__ SplitParams q)
 {
-    for (uint32_t s = blockIdx.x; s < q.n; s += gridDim.x) {
+    for (uint32_t w = blockIdx.x; w < q.n * q.parts; w += gridDim.x) {
+        const uint32_t s = w / q.parts, part = w - s * q.parts;
         const uint32_t len = __ldg(q.block_len + s);
         const uint32_t L = (len + q.k - 1) / q.k, nvec = (L + 15) >> 4;
         const uint8_t *src = q.blocks + (unsigned long long)s * q.block_pitch;
         uint8_t *dst = q.shards + (unsigned long long)s * q.k * q.stride;
-        for (uint32_t idx = threadIdx.x; idx < q.k * nvec; idx += blockDim.x) {
+        const uint32_t total = q.k * nvec, per = ((total + q.parts - 1) / q.parts + 255u) & ~255u;
+        const uint32_t lo = part * per, hi = min(total, lo + per);
+#pragma unroll 4
+        for (uint32_t idx = lo + threadIdx.x; idx < hi; idx += 256) {
             const uint32_t j = idx / nvec, v = idx - j * nvec;
             const uint32_t pos = j * L + v * 16;  // first source byte of this vector
             // valid bytes: inside the shard and inside the block
@@ -1615,10 +1620,10 @@ __global__ void __launch_bounds__(256) split_blocks_kernel(const __grid_constant
             uint4 o = make_uint4(0, 0, 0, 0);
             if (nvalid) {
                 const uint32_t a = pos & ~3u, sh = (pos & 3u) * 8;
-                const uint32_t *w = reinterpret_cast<const uint32_t *>(src + a);
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(src + a);
                 // words a .. a+16 hold bytes pos .. pos+15 (+ up to 3 on either side); the staging buffer is
                 // padded so that reading one word past the block is always inside the allocation
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0;
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0;
                 o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                                __funnelshift_r(w3, w4, sh));
                 if (nvalid < 16) o = mask_tail(o, nvalid);

@@ -174,6 +174,11 @@ void garage_ec_blake2sum(const uint8_t *data, size_t len, uint8_t out32[32]);
 #define GARAGE_EC_SUM_BLAKE2 0
 #define GARAGE_EC_SUM_ADLER8 1
 int garage_ec_set_sum_kind(garage_ec_ctx *ctx, int kind);
+/* How HOST-mode calls of this context wait for the GPU: 0 (default) = cudaStreamSynchronize, the driver
+ * spins on a CPU (lowest latency); 1 = block on an event, the waiting thread sleeps.  For callers that
+ * keep several calls in flight from a small CPU budget -- the batching dispatchers in front of
+ * rpc_put_block: three spinning waiters are three of the ~12 CPUs a host has per GPU.                   */
+int garage_ec_set_wait_mode(garage_ec_ctx *ctx, int blocking);
 int garage_ec_shard_sum_host(int kind, const uint8_t *data, size_t len, uint8_t out32[32]);
 
 /* ---- BLOCK-LEVEL convenience (host memory only) -----------------------------------------
@@ -214,6 +219,11 @@ int garage_ec_host_alloc(garage_ec_ctx *ctx, void **out, size_t bytes);
  * GPU reads (upload landing buffers) or the GPU writes and the CPU hands on without reading; CPU reads
  * from such memory are very slow.  The pages are not snooped during DMA.                              */
 int garage_ec_host_alloc_wc(garage_ec_ctx *ctx, void **out, size_t bytes);
+/* memcpy into a pinned buffer that the GPU reads next (the landing copy of a PUT body, BytesBuf::take_exact,
+ * src/net/bytes_buf.rs:66-117; the survivors of a degraded GET).  Uses non-temporal stores so that the DMA
+ * read finds the bytes in DRAM instead of snooping them out of the writing core's cache (7x faster upload
+ * of freshly written data on the measured hosts).                                                          */
+void garage_ec_copy_for_dma(void *dst_pinned, const void *src, size_t n);
 void garage_ec_host_free(garage_ec_ctx *ctx, void *ptr);
 /* NUMA placement.  On a multi-socket host each GPU hangs off one socket; garage_ec_host_alloc
  * places its pages on that socket's memory node (preferred-node policy + first touch from a CPU

@@ -24,6 +24,11 @@ impl ErasureCoder {
         check(std::ptr::null(), rc)?;       // NODEVICE => node refuses to start in EC mode: no CPU fallback
         Ok(Self { ctx, k, m })
     }
+    /// HOST-mode calls sleep on an event instead of spinning in the driver: for the batch dispatchers,
+    /// which otherwise pin one CPU each while their batch is on the GPU.
+    pub fn set_wait_blocking(&self, blocking: bool) {
+        unsafe { sys::garage_ec_set_wait_mode(self.ctx, blocking as i32) };
+    }
     pub fn shard_len(&self, block_len: usize) -> usize {
         unsafe { sys::garage_ec_shard_len(block_len as u32, self.k as i32) as usize }
     }

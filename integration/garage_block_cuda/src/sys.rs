@@ -75,6 +75,8 @@ extern "C" {
                             want: *const u8, status: *mut i32, shard_len: *const u32, stride: usize,
                             n_stripes: usize) -> c_int;
     pub fn garage_ec_set_sum_kind(ctx: *mut garage_ec_ctx, kind: c_int) -> c_int;
+    pub fn garage_ec_set_wait_mode(ctx: *mut garage_ec_ctx, blocking: c_int) -> c_int;
+    pub fn garage_ec_copy_for_dma(dst_pinned: *mut c_void, src: *const c_void, n: usize);
     pub fn garage_ec_shard_sum_host(kind: c_int, data: *const u8, len: usize, out32: *mut u8) -> c_int;
     pub fn garage_ec_debug_fail_after(ctx: *mut garage_ec_ctx, n_calls: std::os::raw::c_long) -> c_int;
 }

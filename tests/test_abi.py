@@ -106,3 +106,21 @@ def test_rust_shim_declares_every_symbol():
     assert rust == header_decls()
     md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert sorted(set(re.findall(r"pub fn (garage_ec_[a-z0-9_]+)\s*\(", md))) == header_decls()
+
+
+def test_copy_for_dma_is_a_memcpy_for_every_size_and_alignment():
+    """garage_ec_copy_for_dma (non-temporal landing copy) moves exactly the bytes memcpy would: heads, tails,
+    unaligned sources and destinations, sizes around the 4 KiB switch-over and the 64-byte body granule"""
+    import numpy as np
+
+    import garage_b200 as G
+
+    rng = np.random.default_rng(12)
+    src_buf = rng.integers(0, 256, (1 << 21) + 256, dtype=np.uint8)
+    for n in (0, 1, 63, 64, 4095, 4096, 4097, 4096 + 63, 8191, 104858, (1 << 20), (1 << 20) + 17):
+        for so in (0, 1, 15, 33):
+            for do in (0, 1, 16, 63):
+                dst_buf = np.full(n + 256, 0xA5, dtype=np.uint8)
+                G.copy_for_dma(dst_buf[do:do + n], src_buf[so:so + n])
+                assert np.array_equal(dst_buf[do:do + n], src_buf[so:so + n]), (n, so, do)
+                assert (dst_buf[:do] == 0xA5).all() and (dst_buf[do + n:] == 0xA5).all(), (n, so, do)
