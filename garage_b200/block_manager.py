@@ -97,7 +97,7 @@ class BlockManagerError(RuntimeError):
 class BlockManager:
     """Same method names as garage_block::manager::BlockManager where they exist."""
 
-    def __init__(self, k=10, m=4, n_nodes=None, cuda_device=0, batch_max_blocks=64, batch_linger_us=200,
+    def __init__(self, k=10, m=4, n_nodes=None, cuda_device=0, batch_max_blocks=64, batch_linger_us=100,
                  block_ram_buffer_max=256 << 20, data_dir=None, shard_sum_kind=SUM_ADLER8, verify_content_hash=True,
                  data_fsync=False, block_gc_delay_ms=0):
         """block_gc_delay_ms defaults to 0 HERE (tests delete at once); the library's default is the

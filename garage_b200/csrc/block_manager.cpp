@@ -1479,7 +1479,7 @@ void garage_bm_default_config(garage_bm_config *c)
     c->block_size = 1u << 20;               // util/config.rs:273-275
     c->block_ram_buffer_max = 256ull << 20;  // util/config.rs:276-278
     c->batch_max_blocks = 64;
-    c->batch_linger_us = 200;
+    c->batch_linger_us = 100;  // 300 us cost 30 % of the closed-loop PUT rate at 32 callers (r02_summary.md)
     c->data_dir = nullptr;
     c->shard_sum_kind = GARAGE_EC_SUM_ADLER8;
     c->verify_content_hash = 1;
@@ -1537,8 +1537,10 @@ static int bm_create(garage_bm **out, const garage_bm_config *cfg)
         if (rc != GARAGE_EC_OK) return destroy_on_error(rc);
         garage_ec_set_sum_kind(bm->enc_ctx[w], bm->sum_kind);
         garage_ec_set_sum_kind(bm->rec_ctx[w], bm->sum_kind);
-        // the dispatchers sleep while their batch is on the GPU: the CPUs belong to the callers' copies
-        const int sleep_wait = getenv("GARAGE_BM_SPIN_WAIT") ? 0 : 1;  // (=1: spin, for A/B measurements)
+        // Dispatchers wait for their batch spinning in the driver (default) or sleeping on an event
+        // (GARAGE_BM_SLEEP_WAIT=1).  Measured on a 16-CPU box, 32 client threads: 20.0 GiB/s PUT spinning, 16.9
+        // sleeping -- the wake-up latency costs more than the three CPUs (profiles/r02_summary.md).
+        const int sleep_wait = getenv("GARAGE_BM_SLEEP_WAIT") ? 1 : 0;
         garage_ec_set_wait_mode(bm->enc_ctx[w], sleep_wait);
         garage_ec_set_wait_mode(bm->rec_ctx[w], sleep_wait);
         for (auto &eb : bm->enc_out[w]) eb.ctx = bm->enc_ctx[w];

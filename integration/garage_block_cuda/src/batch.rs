@@ -65,9 +65,12 @@ struct ReconReq {
 }
 
 #[derive(Clone)]
-pub struct BatchConfig { pub max_blocks: usize, pub linger: Duration, pub dispatchers: usize, pub block_size: usize }
+pub struct BatchConfig { pub max_blocks: usize, pub linger: Duration, pub dispatchers: usize, pub block_size: usize,
+                         /// dispatchers sleep on an event instead of spinning in the driver while their batch is on the GPU
+                         /// (frees one CPU per dispatcher; measured 15 % lower PUT rate on a 16-CPU host)
+                         pub sleep_wait: bool }
 impl Default for BatchConfig {
-    fn default() -> Self { Self { max_blocks: 64, linger: Duration::from_micros(300), dispatchers: 3, block_size: 1 << 20 } }
+    fn default() -> Self { Self { max_blocks: 64, linger: Duration::from_micros(100), dispatchers: 3, block_size: 1 << 20, sleep_wait: false } }
 }
 
 /// cloneable handle held by BlockManager (next to `buffer_kb_semaphore`, src/block/manager.rs:156)
@@ -84,7 +87,7 @@ pub struct EcBatcher {
 impl EcBatcher {
     pub fn new(ec: Arc<ErasureCoder>, cfg: BatchConfig) -> Self {
         let stride = unsafe { sys::garage_ec_stride_for(ec.shard_len(cfg.block_size) as u32) };
-        ec.set_wait_blocking(true);   // dispatchers sleep while their batch is on the GPU
+        ec.set_wait_blocking(cfg.sleep_wait);
         let (enc_tx, enc_rx) = mpsc::unbounded_channel::<EncodeReq>();
         let (rec_tx, rec_rx) = mpsc::unbounded_channel::<ReconReq>();
         let enc_rx = Arc::new(std::sync::Mutex::new(enc_rx));
