@@ -76,9 +76,10 @@ def build(force=False, verbose=False):
 
 
 BM_SO = os.path.join(PKG, "libgarage_block.so")
-BM_SOURCES = [os.path.join(CSRC, "block_manager.cpp"), os.path.join(CSRC, "shard_wire.cpp")]
+BM_SOURCES = [os.path.join(CSRC, "block_manager.cpp"), os.path.join(CSRC, "shard_wire.cpp"), os.path.join(CSRC, "placement.cpp")]
 BM_DEPS = BM_SOURCES + [os.path.join(ROOT, "include", "garage_block_manager.h"), os.path.join(ROOT, "include", "garage_ec.h"),
-                        os.path.join(ROOT, "include", "garage_shard_wire.h"), os.path.join(CSRC, "blake2b.h")]
+                        os.path.join(ROOT, "include", "garage_shard_wire.h"), os.path.join(ROOT, "include", "garage_placement.h"),
+                        os.path.join(CSRC, "blake2b.h")]
 
 
 def build_block_manager(force=False):

@@ -14,6 +14,7 @@
 // (garage_ec_reconstruct_stripes).  The dispatchers only issue the batch call.
 #include "../../include/garage_block_manager.h"
 #include "../../include/garage_ec.h"
+#include "../../include/garage_placement.h"
 
 #include <algorithm>
 #include <array>
@@ -1044,7 +1045,7 @@ struct garage_bm {
             std::lock_guard<std::mutex> lk(refs_mu);
             refs[h] = (uint32_t)len;
         }
-        const int quorum = std::min(tot, k + 1);
+        const int quorum = garage_ec_write_quorum(k, m, GARAGE_CONSISTENT);  // k+1 capped at k+m (row f4, garage_placement.h)
         return stored >= quorum ? GARAGE_BM_OK : GARAGE_BM_E_QUORUM;
     }
 
