@@ -100,7 +100,7 @@ struct Problem {
 // Vertices: S, T, per partition {up, down}, per (partition, zone) {in, out}, per storage node one.
 // up carries zr units, at most one per zone (so >= zr zones are used); down carries the other rf - zr; a zone's
 // total for one partition is capped between `in` and `out`; out -> node edges carry one shard; a node takes
-// capacity / partition_size partitions.  (Same constraints as the reference's optimiser, version.rs:556-596.)
+// capacity / partition_size partitions.  (Same constraints as the reference's optimiser, version.rs:558-596.)
 struct Graph {
     Flow f;
     int S, T;

@@ -1,7 +1,7 @@
 """Row f4: placement and quorums for erasure-coded blocks, include/garage_placement.h.
 CPU only.  Every property is checked by code in this file that shares nothing with placement.cpp.
 
-Reference behaviour the tests are modelled on: `LayoutVersion::check` (src/rpc/layout/version.rs:170-290:
+Reference behaviour the tests are modelled on: `LayoutVersion::check` (src/rpc/layout/version.rs:177-290:
 distinct nodes per partition, no gateway stores data, zone redundancy, node usage within capacity),
 `partition_of` (:101-104), the `QuorumSetResultTracker` rules (src/rpc/rpc_helper.rs:664-760) and the ordering
 of `block_read_nodes_of` / `request_order` (:570-660)."""
