@@ -798,7 +798,7 @@ def run_e2e(args, torch, dist, enc, dec, rank, world, dev, shards_d, data_d, pre
                                                                     slow["reconstruct_h2d_GBs"], slow["reconstruct_d2h_GBs"]))
     else:
         res["limiter"] = ("%d ranks at %.1f-%.1f GiB/s each (slowest rank %d: encode H2D %.1f GB/s, reconstruct H2D %.1f GB/s); pinned "
-                          "buffers %s. A rank alone on such a host reaches ~41 GiB/s (53 GB/s H2D): a uniform per-rank drop with "
+                          "buffers %s. A rank alone on such a host reaches ~48 GiB/s (53 GB/s H2D staged encode, 50 + 20 GB/s zero-copy reconstruct): a uniform per-rank drop with "
                           "all ranks active and NUMA-local buffers points at the shared host memory / IO system (aggregate DMA "
                           "%.0f GB/s up + %.0f GB/s down), not at placement and not at the kernels"
                           % (world, slow["GiBs"], fast["GiBs"], slow["rank"], slow["encode_h2d_GBs"], slow["reconstruct_h2d_GBs"],
