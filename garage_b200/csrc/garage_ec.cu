@@ -7,6 +7,7 @@
 
 #if defined(__x86_64__)
 #include <emmintrin.h>
+#include <immintrin.h>
 #endif
 #include <cuda_runtime.h>
 
@@ -1300,11 +1301,73 @@ int garage_ec_set_sum_kind(garage_ec_ctx *ctx, int kind)
     return GARAGE_EC_OK;
 }
 
+// Host-side adler8 with AVX2 (the read path checks the tag of every shard it touches: at 2.8 GB/s the scalar loop
+// was a third of the CPU time of a GET in the block manager).  Adler-32 over a run of N = 32 * blocks bytes:
+//   a' = a + sum d,   b' = b + N a + sum_{j,i} (N - 32 j - i) d[j][i]
+// and N - 32 j - i = (32 - i) + 32 (blocks - 1 - j): a weighted sum inside each 32-byte block (pmaddubsw with the
+// taps 32..1) plus 32 times, for every block, the byte sum of all blocks before it.  Runs are capped like zlib's
+// NMAX so that nothing overflows 32 bits.  Same values as adler8_host (blake2b.h) and zlib.adler32.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static uint32_t adler32_avx2(const uint8_t *p, size_t n)
+{
+    uint32_t a = 1, b = 0;
+    const __m256i tap = _mm256_setr_epi8(32, 31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11,
+                                         10, 9, 8, 7, 6, 5, 4, 3, 2, 1);
+    const __m256i ones = _mm256_set1_epi16(1), zero = _mm256_setzero_si256();
+    while (n >= 32) {
+        size_t blocks = n / 32;
+        if (blocks > 5552 / 32) blocks = 5552 / 32;
+        n -= blocks * 32;
+        uint64_t bb = (uint64_t)b + (uint64_t)a * (uint64_t)(blocks * 32);
+        __m256i v_before = zero, v_sum = zero, v_tap = zero;
+        for (size_t j = 0; j < blocks; j++, p += 32) {
+            const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+            v_before = _mm256_add_epi32(v_before, v_sum);
+            v_sum = _mm256_add_epi32(v_sum, _mm256_sad_epu8(d, zero));
+            v_tap = _mm256_add_epi32(v_tap, _mm256_madd_epi16(_mm256_maddubs_epi16(d, tap), ones));
+        }
+        alignas(32) uint32_t s[8], t[8], w[8];
+        _mm256_store_si256(reinterpret_cast<__m256i *>(s), v_sum);
+        _mm256_store_si256(reinterpret_cast<__m256i *>(t), v_tap);
+        _mm256_store_si256(reinterpret_cast<__m256i *>(w), v_before);
+        uint64_t aa = a;
+        for (int i = 0; i < 8; i++) {
+            aa += s[i];
+            bb += (uint64_t)t[i] + 32ull * w[i];
+        }
+        a = (uint32_t)(aa % 65521);
+        b = (uint32_t)(bb % 65521);
+    }
+    for (; n; n--, p++) {
+        a += *p;
+        b += a;
+    }
+    a %= 65521;
+    b %= 65521;
+    return (b << 16) | a;
+}
+
+static void adler8_host_fast(const uint8_t *data, size_t len, uint8_t out[32])
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (!avx2 || len > 0xffffffffull) return adler8_host(data, len, out);
+    const size_t seg = adler8_seg_bytes((uint32_t)len);
+    for (int s = 0; s < 8; s++) {
+        const size_t start = (size_t)s * seg;
+        uint32_t v = 1;  // Adler-32 of nothing
+        if (start < len) v = adler32_avx2(data + start, len < start + seg ? len - start : seg);
+        memcpy(out + 4 * s, &v, 4);  // little endian
+    }
+}
+#else
+static void adler8_host_fast(const uint8_t *data, size_t len, uint8_t out[32]) { adler8_host(data, len, out); }
+#endif
+
 int garage_ec_shard_sum_host(int kind, const uint8_t *data, size_t len, uint8_t out32[32])
 {
     if (!out32 || (!data && len)) return GARAGE_EC_E_INVALID;
     if (kind == GARAGE_EC_SUM_BLAKE2) blake2sum_host(data, len, out32);
-    else if (kind == GARAGE_EC_SUM_ADLER8) adler8_host(data, len, out32);
+    else if (kind == GARAGE_EC_SUM_ADLER8) adler8_host_fast(data, len, out32);
     else return GARAGE_EC_E_INVALID;
     return GARAGE_EC_OK;
 }

@@ -139,6 +139,21 @@ def test_adler8_rfc1950_vector_and_host_function():
     assert G.shard_sum_host(G.SUM_ADLER8, worst) == adler8_ref(worst)
 
 
+def test_adler8_host_vector_path_every_length_class_and_alignment():
+    """the host function runs an AVX2 loop (32-byte blocks, runs of at most 5552 bytes, scalar tails) where the CPU
+    has it: lengths around every boundary of that loop, unaligned starts, all-0xff data (largest sums) and segments
+    spanning many runs, all against zlib"""
+    rng = np.random.default_rng(77)
+    sizes = [31, 32, 33, 63, 64, 65, 255, 256, 257, 8 * 31, 8 * 32, 8 * 33, 5551, 5552, 5553, 8 * 5552 - 1, 8 * 5552, 8 * 5552 + 9,
+             8 * 5536, 8 * 5536 + 32 * 8, 44415, 104857, 262144, (1 << 20) + 13, 3000001]
+    for n in sizes:
+        for fill in ("rand", "ff"):
+            a = rng.integers(0, 256, n, dtype=np.uint8) if fill == "rand" else np.full(n, 255, dtype=np.uint8)
+            for off in (0, 1, 7):
+                b = np.concatenate([np.zeros(off, dtype=np.uint8), a])[off:]  # start at an odd address
+                assert G.shard_sum_host(G.SUM_ADLER8, b) == adler8_ref(a), (n, fill, off)
+
+
 @pytest.mark.gpu
 def test_adler8_device_and_host_paths():
     import torch
