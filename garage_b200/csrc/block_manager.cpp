@@ -740,10 +740,16 @@ struct garage_bm {
 
     size_t shard_len_of(uint32_t block_len) const { return garage_ec_shard_len(block_len, k); }
 
-    // rpc/layout/version.rs:117-137: top 8 bits of the hash -> partition -> k+m distinct nodes
+    // rpc/layout/version.rs:117-137: top 8 bits of the hash -> partition -> k+m distinct nodes, shard i on the
+    // i-th of them.  The ring is a garage_layout (row f4, include/garage_placement.h) filled at create with
+    // partition p -> nodes (p mod n) + i; any other ring (zones, capacities: garage_layout_compute) plugs in here.
+    garage_layout *layout = nullptr;
+    ~garage_bm() { garage_layout_free(layout); }
     void storage_nodes_of(const Hash &h, int *out) const
     {
-        const int n = (int)nodes.size();
+        static_assert(sizeof(int) == sizeof(int32_t), "node ids are 32-bit");
+        if (layout && garage_layout_nodes_of(layout, h.data(), reinterpret_cast<int32_t *>(out)) == GARAGE_LAYOUT_OK) return;
+        const int n = (int)nodes.size();  // more nodes than a ring row can name: the same rule, computed
         const int p = h[0] % n;
         for (int i = 0; i < tot; i++) out[i] = (p + i) % n;
     }
@@ -1506,6 +1512,16 @@ static int bm_create(garage_bm **out, const garage_bm_config *cfg)
     int rc = garage_ec_create(&bm->ec, cfg->cuda_device, k, m, GARAGE_EC_VANDERMONDE);
     if (rc != GARAGE_EC_OK) return rc;  // no GPU => no block manager: there is no CPU fallback
     garage_ec_set_sum_kind(bm->ec, bm->sum_kind);
+    if (cfg->n_nodes <= GARAGE_LAYOUT_MAX_NODES) {
+        const int n = cfg->n_nodes, tot = k + m;
+        std::vector<uint8_t> ring((size_t)GARAGE_NB_PARTITIONS * tot);
+        for (int p = 0; p < GARAGE_NB_PARTITIONS; p++)
+            for (int i = 0; i < tot; i++) ring[(size_t)p * tot + i] = (uint8_t)((p % n + i) % n);
+        std::vector<int32_t> zone(n, 0);
+        std::vector<uint64_t> capacity(n, 1);
+        if (garage_layout_from_ring(&bm->layout, 1, n, zone.data(), capacity.data(), tot, ring.data()) != GARAGE_LAYOUT_OK)
+            bm->layout = nullptr;
+    }
     for (int i = 0; i < cfg->n_nodes; i++) {
         bm->nodes.emplace_back(new Node());
         Node &nd = *bm->nodes.back();

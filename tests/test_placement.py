@@ -396,3 +396,16 @@ def test_gather_simulation_any_m_failures_still_decodable():
         got = {i for n, i, _ in plan if n not in dead}
         assert len(got) == k - 1 + 0 or len(got) < k + m - m  # k+m-(m+1) = k-1 shards are left
         assert len(got) == k - 1
+
+
+def test_the_mirror_ring_is_the_rule_it_replaced():
+    """block_manager.cpp fills a garage_layout with partition p -> nodes (p mod n) + i and asks it for the nodes of a
+    hash; that is node (hash[0] mod n + i) mod n for shard i, the rule the mirror used before it had a layout"""
+    rng = random.Random(11)
+    for n, tot in ((14, 14), (17, 14), (9, 6), (256, 36), (6, 6)):
+        ring = np.array([[(p % n + i) % n for i in range(tot)] for p in range(256)], dtype=np.uint8 if n <= 256 else None)
+        lay = P.Layout.from_ring([0] * n, [1] * n, tot, ring)
+        assert lay.check()[0] == P.OK
+        for _ in range(50):
+            h = bytes(rng.randrange(256) for _ in range(32))
+            assert lay.nodes_of(h) == [(h[0] % n + i) % n for i in range(tot)]
