@@ -1,5 +1,6 @@
 //! Safe wrapper with Garage's conventions.  NOT compiled here.
 pub mod batch;   // the batching front-end (row f1): EcBatcher::encode / ::reconstruct are what BlockManager calls
+pub mod placement;   // row f4: shard-aware nodes_of / write sets / read plan (pure Rust, belongs in garage_rpc)
 pub mod sys;
 
 use bytes::Bytes;
