@@ -409,3 +409,52 @@ def test_the_mirror_ring_is_the_rule_it_replaced():
         for _ in range(50):
             h = bytes(rng.randrange(256) for _ in range(32))
             assert lay.nodes_of(h) == [(h[0] % n + i) % n for i in range(tot)]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_clusters_and_layout_changes(seed):
+    """random zones / capacities / codes: every computed ring satisfies the constraints (independent checker), the load
+    follows the capacities, and a follow-up layout after nodes left or joined keeps shard indices and moves at most a
+    small multiple of what the departed nodes held"""
+    rng = random.Random(1000 + seed)
+    n = rng.randrange(8, 40)
+    nz = rng.randrange(1, 7)
+    rf = rng.choice([3, 6, 9, 14])
+    if rf > n:
+        rf = n
+    zones = [rng.randrange(nz) for _ in range(n)]
+    caps = [rng.choice([0, 1, 1, 2, 4]) * 10**12 for _ in range(n)]
+    storage = [i for i in range(n) if caps[i]]
+    real_zones = len({zones[i] for i in storage})
+    mpz = rng.choice([0, 0, max(1, -(-rf // max(real_zones, 1)) + 1)])
+    try:
+        v1 = P.Layout.compute(zones, caps, rf, max_per_zone=mpz)
+    except P.PlacementError as e:
+        assert e.code == P.E_INFEASIBLE
+        return  # (too few storage nodes, a zone limit that cannot be met, or capacities too skewed)
+    zr = min(real_zones, rf)
+    load = independent_check(v1.ring(), zones, caps, zr, mpz, v1.partition_size)
+    assert load.sum() == 256 * rf
+    # load follows capacity: nobody is more than one partition-size step above its share of the bytes
+    for i in storage:
+        assert load[i] <= caps[i] // v1.partition_size
+    # change: one storage node leaves, one gateway (if any) gets capacity
+    caps2 = list(caps)
+    gone = rng.choice(storage)
+    caps2[gone] = 0
+    gw = [i for i in range(n) if caps[i] == 0]
+    if gw:
+        caps2[rng.choice(gw)] = 2 * 10**12
+    try:
+        v2 = P.Layout.compute(zones, caps2, rf, max_per_zone=mpz, previous=v1, version=2)
+    except P.PlacementError as e:
+        assert e.code == P.E_INFEASIBLE
+        return
+    real_zones2 = len({zones[i] for i in range(n) if caps2[i]})
+    independent_check(v2.ring(), zones, caps2, min(real_zones2, rf), mpz, v2.partition_size)
+    r1, r2 = v1.ring(), v2.ring()
+    for p in range(256):
+        for i in range(rf):
+            if r1[p][i] in r2[p]:
+                assert list(r2[p]).index(r1[p][i]) == i
+    assert v1.transition_to(v2) == int((r1 != r2).sum())
